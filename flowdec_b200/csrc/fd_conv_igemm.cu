@@ -1,0 +1,427 @@
+// flowdec_b200 — 3x3 / 1x1 convolution as a tcgen05 implicit GEMM (sm_100a).
+//
+// Replaces, for the NCSN++ backbone of FlowDec, what the reference runs as
+// `nn.Conv2d` -> cuDNN (reference: flowdec/backbones/ncsnpp_utils/layers.py:110-134,
+// used from layerspp.py:235,243,245 and ncsnpp.py:162,218,230).  64 convolutions per
+// backbone forward carry 99.9 % of the arithmetic.
+//
+// Formulation
+//   activations  NHWC bf16   [B, H, W, C]           (H = frequency, W = time)
+//   weights      bf16        [Npad, Ktot]  K-major  (packed once at load time)
+//   GEMM         D[pixel, cout] = sum_k A[pixel, k] * Wp[cout, k]
+//   k runs over "segments": each segment is one source tensor read through 1 or 9
+//   taps.  A 3x3 conv is one 9-tap segment; a res-block's second conv plus its
+//   1x1 (or identity) skip is a 9-tap segment followed by 1-tap segments, so the
+//   residual add happens inside the TMEM accumulator (layerspp.py:278-284).
+//
+// Kernel structure (one persistent CTA per SM, 192 threads)
+//   warp 0      TMA producer: per k-step one 4-D box load of A (128 pixels x 64
+//               channels, shifted by the tap; out-of-image coordinates are
+//               zero-filled by TMA = the conv's zero padding) and one 2-D box load of
+//               the weight slice, into a STAGES-deep 128B-swizzled smem ring.
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=Npad, K=16,
+//               fp32 accumulators in TMEM, double-buffered (2 x Npad columns).
+//   warps 2..5  epilogue: tcgen05.ld -> +bias -> bf16 -> swizzled smem -> TMA store
+//               (or fp32 direct stores for the 4-channel pyramid convs).
+#include "fd_common.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace fd {
+
+constexpr int kMaxSeg = 4;
+constexpr int kTileM = 128;   // pixels per tile (= UMMA M)
+constexpr int kSliceK = 64;   // channels per k-step (= one 128-byte swizzle span of bf16)
+constexpr int kABytes = kTileM * kSliceK * 2;
+
+struct ConvParams {
+  CUtensorMap a_map[kMaxSeg];
+  CUtensorMap b_map;
+  CUtensorMap out_map;
+  int nseg;
+  int seg_kslices[kMaxSeg];
+  int seg_taps[kMaxSeg];
+  int B, H, W;
+  int bh, bw;            // tile = bh x bw pixels, bh*bw == 128
+  int tiles_h, tiles_w;
+  int num_tiles;
+  const float* bias;     // [Npad] or nullptr
+  float* out_f32;        // fp32 NHWC [B,H,W,cout_valid] (OUT_F32 kernels only)
+  int cout_valid;
+};
+
+template <int N>
+struct ConvCfg {
+  static constexpr int kStages = (N == 256) ? 4 : (N == 128 ? 6 : 8);
+  static constexpr int kBBytes = N * kSliceK * 2;
+  static constexpr int kOutBytes = (N >= 64) ? 2 * kTileM * 128 : 0;  // two 64-channel staging tiles
+  static constexpr int kTmemCols = (2 * N <= 32) ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes =
+      1024 + kStages * (kABytes + kBBytes) + kOutBytes + N * 4 + 256;
+};
+
+template <int N, bool OUT_F32>
+__global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<N>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int B_BYTES = Cfg::kBBytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * kABytes;
+  uint8_t* sOut = sB + STAGES * B_BYTES;
+  float* sBias = reinterpret_cast<float*>(sOut + Cfg::kOutBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + N);
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sBias[i] = p.bias ? p.bias[i] : 0.0f;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    fence_mbar_init();
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.a_map[s]);
+    tma_prefetch_desc(&p.b_map);
+    if (!OUT_F32) tma_prefetch_desc(&p.out_map);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int k_iters = 0;
+  for (int s = 0; s < p.nseg; ++s) k_iters += p.seg_kslices[s] * p.seg_taps[s];
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.bh;
+        const int w0 = (rem % p.tiles_w) * p.bw;
+        int kb = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int taps = p.seg_taps[s];
+          const int ksl = p.seg_kslices[s];
+          for (int t = 0; t < taps; ++t) {
+            const int dh = (taps == 9) ? (t / 3 - 1) : 0;
+            const int dw = (taps == 9) ? (t % 3 - 1) : 0;
+            for (int ks = 0; ks < ksl; ++ks) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_expect_tx(&full_bar[stage], kABytes + B_BYTES);
+              tma_load_4d(sA + stage * kABytes, &p.a_map[s], &full_bar[stage], ks * kSliceK,
+                          w0 + dw, h0 + dh, n);
+              tma_load_2d(sB + stage * B_BYTES, &p.b_map, &full_bar[stage], kb * kSliceK, 0);
+              ++kb;
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * N);
+        for (int ki = 0; ki < k_iters; ++ki) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * kABytes));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < kSliceK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128-byte swizzle span (encoded >>4)
+            umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                      idesc, static_cast<uint32_t>((ki | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int ew = warp & 3;               // TMEM lane quarter this warp may read
+    const int row = ew * 32 + lane;        // pixel row of the tile
+    const bool leader = (threadIdx.x == 64);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * p.bh;
+      const int w0 = (rem % p.tiles_w) * p.bw;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                             static_cast<uint32_t>(acc * N);
+      if constexpr (OUT_F32) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row, v);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&tempty_bar[acc]);
+        const int hl = row / p.bw;
+        const int wl = row - hl * p.bw;
+        const size_t pix = (static_cast<size_t>(n) * p.H + (h0 + hl)) * p.W + (w0 + wl);
+        float* o = p.out_f32 + pix * p.cout_valid;
+        if (p.cout_valid == 4) {
+          float4 r;
+          r.x = __uint_as_float(v[0]) + sBias[0];
+          r.y = __uint_as_float(v[1]) + sBias[1];
+          r.z = __uint_as_float(v[2]) + sBias[2];
+          r.w = __uint_as_float(v[3]) + sBias[3];
+          *reinterpret_cast<float4*>(o) = r;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < p.cout_valid) o[c] = __uint_as_float(v[c]) + sBias[c];
+        }
+      } else {
+        constexpr int kChunks = N / 64;
+#pragma unroll 1
+        for (int ch = 0; ch < kChunks; ++ch) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(t_row + ch * 64, v0);
+          tmem_ld_32x32b_x32(t_row + ch * 64 + 32, v1);
+          tmem_ld_wait();
+          if (ch == kChunks - 1) {
+            tc_fence_before_sync();
+            mbar_arrive(&tempty_bar[acc]);
+          }
+          uint8_t* stg = sOut + (ch & 1) * (kTileM * 128);
+          // the TMA store that last read this staging tile must have drained it
+          if (leader) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          const float* bs = sBias + ch * 64;
+          uint8_t* rowp = stg + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 q;
+            q.x = pack_bf16x2(__uint_as_float(v0[8 * j + 0]) + bs[8 * j + 0],
+                              __uint_as_float(v0[8 * j + 1]) + bs[8 * j + 1]);
+            q.y = pack_bf16x2(__uint_as_float(v0[8 * j + 2]) + bs[8 * j + 2],
+                              __uint_as_float(v0[8 * j + 3]) + bs[8 * j + 3]);
+            q.z = pack_bf16x2(__uint_as_float(v0[8 * j + 4]) + bs[8 * j + 4],
+                              __uint_as_float(v0[8 * j + 5]) + bs[8 * j + 5]);
+            q.w = pack_bf16x2(__uint_as_float(v0[8 * j + 6]) + bs[8 * j + 6],
+                              __uint_as_float(v0[8 * j + 7]) + bs[8 * j + 7]);
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = q;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 q;
+            q.x = pack_bf16x2(__uint_as_float(v1[8 * j + 0]) + bs[32 + 8 * j + 0],
+                              __uint_as_float(v1[8 * j + 1]) + bs[32 + 8 * j + 1]);
+            q.y = pack_bf16x2(__uint_as_float(v1[8 * j + 2]) + bs[32 + 8 * j + 2],
+                              __uint_as_float(v1[8 * j + 3]) + bs[32 + 8 * j + 3]);
+            q.z = pack_bf16x2(__uint_as_float(v1[8 * j + 4]) + bs[32 + 8 * j + 4],
+                              __uint_as_float(v1[8 * j + 5]) + bs[32 + 8 * j + 5]);
+            q.w = pack_bf16x2(__uint_as_float(v1[8 * j + 6]) + bs[32 + 8 * j + 6],
+                              __uint_as_float(v1[8 * j + 7]) + bs[32 + 8 * j + 7]);
+            *reinterpret_cast<uint4*>(rowp + (((j + 4) ^ (row & 7)) << 4)) = q;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (leader) {
+            tma_store_4d(&p.out_map, stg, ch * 64, w0, h0, n);
+            tma_store_commit();
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (!OUT_F32 && leader) tma_store_wait_all<0>();
+  }
+
+  __syncwarp();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+// NHWC bf16 tensor [B,H,W,Ctot]; the map exposes channels [c_begin, c_begin + c_count)
+static int make_nhwc_map(CUtensorMap* m, const void* base, int B, int H, int W, int Ctot,
+                         int c_begin, int c_count, int bh, int bw) {
+  EncodeTiledFn enc = get_encode_fn();
+  FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  FD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (c_begin % 8) == 0 && (Ctot % 8) == 0,
+             "NHWC tensor must be 16-byte aligned with channel counts that are multiples of 8");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(c_count), static_cast<cuuint64_t>(W),
+                        static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(Ctot) * 2,
+                           static_cast<cuuint64_t>(W) * Ctot * 2,
+                           static_cast<cuuint64_t>(H) * W * Ctot * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kSliceK), static_cast<cuuint32_t>(bw),
+                       static_cast<cuuint32_t>(bh), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  void* addr = const_cast<uint8_t*>(static_cast<const uint8_t*>(base)) + static_cast<size_t>(c_begin) * 2;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, addr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(NHWC) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+static int make_weight_map(CUtensorMap* m, const void* base, int npad, int ktot) {
+  EncodeTiledFn enc = get_encode_fn();
+  FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(npad)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kSliceK), static_cast<cuuint32_t>(npad)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+template <int N, bool OUT_F32>
+static int launch_conv(const ConvParams& p, int max_ctas, cudaStream_t stream) {
+  auto kern = conv_igemm_kernel<N, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ConvCfg<N>::kSmemBytes);
+    FD_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", ConvCfg<N>::kSmemBytes,
+               cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int grid = std::min(p.num_tiles, max_ctas > 0 ? max_ctas : device_sm_count());
+  kern<<<grid, 192, ConvCfg<N>::kSmemBytes, stream>>>(p);
+  return check_launch("fd_conv2d_igemm");
+}
+
+}  // namespace fd
+
+// ---------------------------------------------------------------------------------
+// C ABI (declared in include/flowdec_b200.h)
+// ---------------------------------------------------------------------------------
+struct fd_conv_src {
+  const void* ptr;  // bf16 NHWC [B,H,W,C]
+  int C;            // channel pitch of the tensor
+  int c_begin;      // first channel consumed
+  int c_count;      // channels consumed (multiple of 64)
+  int taps;         // 1 or 9
+};
+
+extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot,
+                               const float* bias, void* out, int out_is_f32, int cout, int npad,
+                               int B, int H, int W, int max_ctas, cudaStream_t stream) {
+  using namespace fd;
+  FD_REQUIRE(nsrc >= 1 && nsrc <= kMaxSeg, "fd_conv2d_igemm: nsrc=%d out of range [1,%d]", nsrc, kMaxSeg);
+  FD_REQUIRE(npad == 16 || npad == 128 || npad == 256, "fd_conv2d_igemm: npad=%d unsupported", npad);
+  FD_REQUIRE(W % 8 == 0 && W >= 8, "fd_conv2d_igemm: W=%d must be a multiple of 8", W);
+  int bw = 8;
+  while (bw < 128 && W % (bw * 2) == 0) bw *= 2;
+  const int bh = kTileM / bw;
+  FD_REQUIRE(H % bh == 0, "fd_conv2d_igemm: H=%d not divisible by tile height %d", H, bh);
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.nseg = nsrc;
+  int ksum = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    FD_REQUIRE(srcs[s].taps == 1 || srcs[s].taps == 9, "fd_conv2d_igemm: taps must be 1 or 9");
+    FD_REQUIRE(srcs[s].c_count % kSliceK == 0 && srcs[s].c_count > 0,
+               "fd_conv2d_igemm: segment channel count %d not a multiple of 64", srcs[s].c_count);
+    p.seg_kslices[s] = srcs[s].c_count / kSliceK;
+    p.seg_taps[s] = srcs[s].taps;
+    ksum += srcs[s].c_count * srcs[s].taps;
+    if (make_nhwc_map(&p.a_map[s], srcs[s].ptr, B, H, W, srcs[s].C, srcs[s].c_begin,
+                      srcs[s].c_count, bh, bw))
+      return 1;
+  }
+  FD_REQUIRE(ksum == ktot, "fd_conv2d_igemm: packed K=%d does not match segments (%d)", ktot, ksum);
+  if (make_weight_map(&p.b_map, wpacked, npad, ktot)) return 1;
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  p.bh = bh;
+  p.bw = bw;
+  p.tiles_h = H / bh;
+  p.tiles_w = W / bw;
+  p.num_tiles = B * p.tiles_h * p.tiles_w;
+  p.bias = bias;
+  p.cout_valid = cout;
+  if (out_is_f32) {
+    FD_REQUIRE(npad == 16 && cout >= 1 && cout <= 16, "fd_conv2d_igemm: fp32 output needs npad=16");
+    p.out_f32 = static_cast<float*>(out);
+    return launch_conv<16, true>(p, max_ctas, stream);
+  }
+  FD_REQUIRE(cout == npad && npad >= 128, "fd_conv2d_igemm: bf16 output needs cout == npad in {128,256}");
+  if (make_nhwc_map(&p.out_map, out, B, H, W, cout, 0, cout, bh, bw)) return 1;
+  if (npad == 256) return launch_conv<256, false>(p, max_ctas, stream);
+  return launch_conv<128, false>(p, max_ctas, stream);
+}

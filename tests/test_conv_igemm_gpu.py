@@ -1,0 +1,99 @@
+"""GPU parity: tcgen05 implicit-GEMM conv (fd_conv2d_igemm) vs torch F.conv2d in fp32 on
+the same bf16-rounded operands.  Tolerance: fp32-accumulation-order noise + one bf16
+output rounding (rel 2^-8), i.e. |err| <= 1e-2 * max|ref| elementwise is generous while any
+descriptor/layout bug produces O(1) errors."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from flowdec_b200 import _lib
+from flowdec_b200.ops import conv_igemm, pack_conv_weight
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_conv(x_nhwc_bf16, w_oihw_bf16, bias):
+    x = x_nhwc_bf16.float().permute(0, 3, 1, 2)
+    y = F.conv2d(x, w_oihw_bf16.float(), bias, padding=w_oihw_bf16.shape[-1] // 2)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [
+    (1, 16, 16, 64, 256, 1),
+    (1, 16, 16, 64, 256, 3),
+    (2, 96, 8, 256, 128, 3),
+    (1, 32, 64, 128, 256, 3),
+    (2, 24, 128, 256, 256, 3),
+    (1, 16, 256, 512, 256, 3),
+    (3, 48, 24, 384, 128, 3),
+])
+def test_conv_single_segment(B, H, W, Cin, Cout, k):
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, device=dev)
+    wp = pack_conv_weight([(w, k * k)], npad=Cout)
+    out = torch.empty(B, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    conv_igemm([(x, 0, Cin, k * k)], wp, b, out)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, b)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item() + 1e-3, err
+
+
+def test_conv_two_sources_plus_skip():
+    """conv1 (3x3 on a) + 1x1 skip on the virtual concat [xa, xb] accumulated in one TMEM tile"""
+    torch.manual_seed(1)
+    dev = "cuda"
+    B, H, W = 2, 32, 32
+    a = torch.randn(B, H, W, 256, device=dev).to(torch.bfloat16)
+    xa = torch.randn(B, H, W, 256, device=dev).to(torch.bfloat16)
+    xb = torch.randn(B, H, W, 64, device=dev).to(torch.bfloat16)
+    w1 = (torch.randn(256, 256, 3, 3, device=dev) / 48).to(torch.bfloat16)
+    w2 = (torch.randn(256, 320, 1, 1, device=dev) / 18).to(torch.bfloat16)
+    b = torch.randn(256, device=dev)
+    wp = pack_conv_weight([(w1, 9), (w2[:, :256], 1), (w2[:, 256:], 1)], npad=256)
+    out = torch.empty(B, H, W, 256, device=dev, dtype=torch.bfloat16)
+    conv_igemm([(a, 0, 256, 9), (xa, 0, 256, 1), (xb, 0, 64, 1)], wp, b, out)
+    torch.cuda.synchronize()
+    ref = _ref_conv(a, w1, b) + _ref_conv(torch.cat([xa, xb], -1), w2, None)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item() + 1e-3, err
+
+
+def test_conv_f32_out_4ch():
+    torch.manual_seed(2)
+    dev = "cuda"
+    B, H, W, Cin = 2, 48, 16, 256
+    x = torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16)
+    w = (torch.randn(4, Cin, 3, 3, device=dev) / 48).to(torch.bfloat16)
+    b = torch.randn(4, device=dev)
+    wp = pack_conv_weight([(w, 9)], npad=16)
+    bias16 = torch.zeros(16, device=dev)
+    bias16[:4] = b
+    out = torch.empty(B, H, W, 4, device=dev, dtype=torch.float32)
+    conv_igemm([(x, 0, Cin, 9)], wp, bias16, out)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, b)
+    err = (out - ref).abs().max().item()
+    assert err <= 1e-4 * ref.abs().max().item() + 1e-4, err
+
+
+def test_conv_many_tiles_persistent():
+    """more tiles than SMs -> exercises the TMEM double buffer and the smem ring wrap"""
+    torch.manual_seed(3)
+    dev = "cuda"
+    B, H, W, C = 4, 96, 128, 256
+    x = torch.randn(B, H, W, C, device=dev).to(torch.bfloat16)
+    w = (torch.randn(C, C, 3, 3, device=dev) / 48).to(torch.bfloat16)
+    b = torch.randn(C, device=dev)
+    wp = pack_conv_weight([(w, 9)], npad=C)
+    out = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
+    conv_igemm([(x, 0, C, 9)], wp, b, out)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, b)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item() + 1e-3, err
