@@ -28,6 +28,35 @@ class ConvSrc(ctypes.Structure):
     ]
 
 
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+_D = ctypes.c_double
+_Z = ctypes.c_size_t
+
+# One entry per `extern "C"` function declared in include/flowdec_b200.h (same order).
+SIGNATURES = {
+    "fd_abi_version": [],
+    "fd_conv2d_igemm": [ctypes.POINTER(ConvSrc), _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "fd_chan_stats": [_P, _I, _I, _I, _P, _I, _P],
+    "fd_gn_finalize": [_P, _I, _P, _I, _I, _I, _D, _P, _P, _I, _F, _P, _P],
+    "fd_gn_act_resample": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
+    "fd_pack4": [_P, _P, _P, _Z, _P],
+    "fd_fir_down4": [_P, _P, _I, _I, _I, _P],
+    "fd_pyramid_up_add": [_P, _P, _P, _I, _I, _I, _P],
+    "fd_conv_in": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "fd_combine": [_P, _P, _P, _P, _P, _Z, _I, _P],
+    "fd_output_axpy": [_P, ctypes.POINTER(ctypes.c_float), _P, _F, _P, _F, _F, _P, _P, _Z, _P],
+    "fd_x0": [_P, _P, _P, _F, _P, _I, _I, _I, _P],
+    "fd_fourier_embed": [_F, _P, _I, _P, _P],
+    "fd_matvec": [_P, _I, _I, _P, _P, _P, _F, _P, _I, _P],
+    "fd_twiddles1534": [_P, _P],
+    "fd_normfac": [_P, _I, _I, _I, _P, _P],
+    "fd_stft1534_compress": [_P, _I, _I, _P, _P, _P, _F, _F, _I, _P, _P],
+    "fd_istft1534_decompress": [_P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P],
+}
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -37,7 +66,10 @@ def lib():
                 "(flowdec_b200 has no CPU or PyTorch fallback path)")
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.fd_last_error.restype = ctypes.c_char_p
-        _lib.fd_abi_version.restype = ctypes.c_int
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(_lib, name)          # AttributeError here = header / library mismatch
+            fn.restype = ctypes.c_int
+            fn.argtypes = argtypes
     return _lib
 
 

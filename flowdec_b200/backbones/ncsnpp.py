@@ -1,0 +1,431 @@
+"""NCSN++ score/velocity backbone of FlowDec, B200-native execution.
+
+Drop-in for the reference class `flowdec.backbones.ncsnpp.NCSNpp`
+(/root/reference/flowdec/backbones/ncsnpp.py:52-411): same constructor keywords, same
+`all_modules.{i}.*` / `output_layer.weight` parameter names and shapes (so
+`load_state_dict(ckpt['_pl_ema_state_dict'])` works unchanged), same
+`forward(x, y, t) -> complex64 [B,1,F,T]` contract.
+
+The nn.Modules below only *hold parameters*.  `forward` never calls their `forward`: it walks
+the network issuing the hand-written sm_100a kernels of libflowdec_b200.so through
+`flowdec_b200.ops` (tcgen05 implicit-GEMM convolutions + HBM-bound GroupNorm/SiLU/FIR
+passes).  Supported configuration family = the one FlowDec ships
+(config/model/backbone/ncsnpp_final_no_attn.yaml): biggan res-blocks, FIR resampling,
+progressive output_skip / input_skip with 'sum' combine, Fourier embedding, no attention.
+Anything else raises NotImplementedError rather than silently running a different path.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+DEFAULT_OUTPUTLAYER_KWARGS = dict(kernel_size=3, bias=False, padding="same", padding_mode="zeros")
+
+
+def _ddpm_uniform_(w, scale=1.0):
+    """variance_scaling(scale, 'fan_avg', 'uniform') of reference layers.py:64-101."""
+    scale = 1e-10 if scale == 0 else scale
+    shape = w.shape
+    rf = float(np.prod(shape)) / shape[1] / shape[0]
+    fan_in, fan_out = shape[1] * rf, shape[0] * rf
+    lim = math.sqrt(3 * scale / ((fan_in + fan_out) / 2))
+    with torch.no_grad():
+        w.uniform_(-lim, lim)
+    return w
+
+
+def _conv(cin, cout, k, init_scale=1.0, bias=True):
+    c = nn.Conv2d(cin, cout, kernel_size=k, padding=k // 2, bias=bias)
+    _ddpm_uniform_(c.weight, init_scale)
+    if bias:
+        nn.init.zeros_(c.bias)
+    return c
+
+
+def _dense(cin, cout):
+    d = nn.Linear(cin, cout)
+    _ddpm_uniform_(d.weight)
+    nn.init.zeros_(d.bias)
+    return d
+
+
+class GaussianFourierProjection(nn.Module):
+    """parameter holder for reference layerspp.py:42-51"""
+
+    def __init__(self, embedding_size=256, scale=1.0):
+        super().__init__()
+        self.W = nn.Parameter(torch.randn(embedding_size) * scale, requires_grad=False)
+
+
+class ResnetBlockBigGANpp(nn.Module):
+    """parameter holder for reference layerspp.py:222-284"""
+
+    def __init__(self, in_ch, out_ch=None, temb_dim=None, up=False, down=False, init_scale=0.0):
+        super().__init__()
+        out_ch = out_ch if out_ch else in_ch
+        self.GroupNorm_0 = nn.GroupNorm(min(in_ch // 4, 32), in_ch, eps=1e-6)
+        self.Conv_0 = _conv(in_ch, out_ch, 3)
+        if temb_dim is not None:
+            self.Dense_0 = _dense(temb_dim, out_ch)
+        self.GroupNorm_1 = nn.GroupNorm(min(out_ch // 4, 32), out_ch, eps=1e-6)
+        self.Conv_1 = _conv(out_ch, out_ch, 3, init_scale=init_scale)
+        if in_ch != out_ch or up or down:
+            self.Conv_2 = _conv(in_ch, out_ch, 1)
+        self.up, self.down, self.in_ch, self.out_ch = up, down, in_ch, out_ch
+
+
+class Combine(nn.Module):
+    """parameter holder for reference layerspp.py:54-69 (method='sum')"""
+
+    def __init__(self, dim1, dim2):
+        super().__init__()
+        self.Conv_0 = _conv(dim1, dim2, 1)
+
+
+class _Workspace:
+    """Named device buffers with stable addresses (CUDA-graph friendly, no per-call allocation)."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, name, shape, dtype, device):
+        key = (name, tuple(shape), dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self.bufs[key] = t
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+class NCSNpp(nn.Module):
+    """NCSN++ model (FlowDec configuration family) running on hand-written sm_100a kernels."""
+
+    def __init__(self,
+                 nonlinearity="swish", nf=128, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2,
+                 attn_resolutions=(64, 32, 16, 8), resamp_with_conv=True, conditional=True, fir=True,
+                 fir_kernel=(1, 3, 3, 1), skip_rescale=True, resblock_type="biggan",
+                 progressive="output_skip", progressive_input="input_skip", progressive_combine="sum",
+                 init_scale=0.0, fourier_scale=16, image_size=256, embedding_type="fourier", dropout=0.0,
+                 num_channels=4, output_layer_kwargs: dict = DEFAULT_OUTPUTLAYER_KWARGS,
+                 bottleneck_attn: bool = True):
+        super().__init__()
+        ch_mult = list(ch_mult)
+        all_res = [image_size // (2 ** i) for i in range(len(ch_mult))]
+        unsupported = []
+        if nonlinearity != "swish": unsupported.append(f"nonlinearity={nonlinearity}")
+        if any(r in list(attn_resolutions) for r in all_res): unsupported.append("attn_resolutions")
+        if bottleneck_attn: unsupported.append("bottleneck_attn=True")
+        if not conditional: unsupported.append("conditional=False")
+        if not fir or list(fir_kernel) != [1, 3, 3, 1]: unsupported.append("fir/fir_kernel")
+        if not skip_rescale: unsupported.append("skip_rescale=False")
+        if resblock_type.lower() != "biggan": unsupported.append(f"resblock_type={resblock_type}")
+        if progressive.lower() != "output_skip": unsupported.append(f"progressive={progressive}")
+        if progressive_input.lower() != "input_skip": unsupported.append(f"progressive_input={progressive_input}")
+        if progressive_combine.lower() != "sum": unsupported.append(f"progressive_combine={progressive_combine}")
+        if embedding_type.lower() != "fourier": unsupported.append(f"embedding_type={embedding_type}")
+        if dropout != 0.0: unsupported.append("dropout")
+        if num_channels != 4: unsupported.append("num_channels")
+        if dict(output_layer_kwargs).get("kernel_size", 3) != 1 or dict(output_layer_kwargs).get("bias", False):
+            unsupported.append("output_layer_kwargs (need 1x1, no bias)")
+        if unsupported:
+            raise NotImplementedError(
+                "flowdec_b200.NCSNpp implements the FlowDec configuration family "
+                "(ncsnpp_final_no_attn.yaml); unsupported: " + ", ".join(unsupported))
+
+        self.nf, self.ch_mult, self.num_res_blocks = nf, ch_mult, num_res_blocks
+        self.num_resolutions = len(ch_mult)
+        self.image_size = image_size
+        self.output_layer = nn.Conv2d(num_channels, 2, kernel_size=1, bias=False)
+
+        # --- module list in the reference's construction order (ncsnpp.py:102-252) ---
+        mods = [GaussianFourierProjection(embedding_size=nf, scale=fourier_scale),
+                _dense(2 * nf, 4 * nf), _dense(4 * nf, 4 * nf), _conv(num_channels, nf, 3)]
+        RB = lambda **kw: ResnetBlockBigGANpp(temb_dim=4 * nf, init_scale=init_scale, **kw)
+        hs_c = [nf]
+        in_ch = nf
+        for lvl in range(self.num_resolutions):
+            for _ in range(num_res_blocks):
+                out_ch = nf * ch_mult[lvl]
+                mods.append(RB(in_ch=in_ch, out_ch=out_ch))
+                in_ch = out_ch
+                hs_c.append(in_ch)
+            if lvl != self.num_resolutions - 1:
+                mods.append(RB(down=True, in_ch=in_ch))
+                mods.append(Combine(dim1=num_channels, dim2=in_ch))
+                hs_c.append(in_ch)
+        in_ch = hs_c[-1]
+        mods.append(RB(in_ch=in_ch))
+        mods.append(RB(in_ch=in_ch))
+        for lvl in reversed(range(self.num_resolutions)):
+            for _ in range(num_res_blocks + 1):
+                out_ch = nf * ch_mult[lvl]
+                mods.append(RB(in_ch=in_ch + hs_c.pop(), out_ch=out_ch))
+                in_ch = out_ch
+            mods.append(nn.GroupNorm(min(in_ch // 4, 32), in_ch, eps=1e-6))
+            mods.append(_conv(in_ch, num_channels, 3, init_scale=init_scale))
+            if lvl != 0:
+                mods.append(RB(in_ch=in_ch, up=True))
+        assert not hs_c
+        self.all_modules = nn.ModuleList(mods)
+
+        self._prepared = None      # packed weights (built lazily, dropped on load_state_dict / .to())
+        self._temb_cache = {}
+        self._ws = _Workspace()
+        self.stats_slabs = 64
+        self.max_ctas = 0
+
+    # ------------------------------------------------------------------ parameter management
+    def _invalidate(self):
+        self._prepared = None
+        self._temb_cache = {}
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._invalidate()
+        return r
+
+    def _load_from_state_dict(self, *a, **k):
+        self._invalidate()
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
+        self._ws = _Workspace()
+        return super()._apply(fn, *a, **k)
+
+    @staticmethod
+    def _npad(cout):
+        if cout <= 16:
+            return 16
+        if cout in (128, 256):
+            return cout
+        raise NotImplementedError(f"tcgen05 conv tile for Cout={cout} not instantiated (16/128/256)")
+
+    def prepare(self):
+        """Repack weights for the kernels (OIHW fp32 -> K-major bf16 [Npad, Ktot], fused skips)."""
+        if self._prepared is not None:
+            return self._prepared
+        dev = self.output_layer.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("flowdec_b200.NCSNpp runs on CUDA (sm_100a) only; call .cuda() first")
+        P = {}
+        inv = 1.0 / math.sqrt(2.0)
+        with torch.no_grad():
+            for i, m in enumerate(self.all_modules):
+                if isinstance(m, ResnetBlockBigGANpp):
+                    e = {}
+                    cin, cout = m.in_ch, m.out_ch
+                    e["w0"] = ops.pack_conv_weight([(m.Conv_0.weight.float(), 9)], self._npad(cout))
+                    e["b0"] = m.Conv_0.bias.float().contiguous()
+                    w1 = m.Conv_1.weight.float() * inv
+                    if hasattr(m, "Conv_2"):
+                        w2 = m.Conv_2.weight.float() * inv       # [cout, cin, 1, 1]
+                        e["w2_full"] = w2
+                        e["b1"] = ((m.Conv_1.bias + m.Conv_2.bias).float() * inv).contiguous()
+                    else:
+                        w2 = (torch.eye(cout, device=dev) * inv).reshape(cout, cout, 1, 1)
+                        e["w2_full"] = w2
+                        e["b1"] = (m.Conv_1.bias.float() * inv).contiguous()
+                    e["w1_conv"] = w1
+                    e["w1_cache"] = {}
+                    e["g0"], e["be0"] = m.GroupNorm_0.weight.float().contiguous(), m.GroupNorm_0.bias.float().contiguous()
+                    e["g1"], e["be1"] = m.GroupNorm_1.weight.float().contiguous(), m.GroupNorm_1.bias.float().contiguous()
+                    e["dw"], e["db"] = m.Dense_0.weight.float().contiguous(), m.Dense_0.bias.float().contiguous()
+                    P[i] = e
+                elif isinstance(m, Combine):
+                    P[i] = dict(w=m.Conv_0.weight.float().reshape(m.Conv_0.weight.shape[0], 4).contiguous(),
+                                b=m.Conv_0.bias.float().contiguous())
+                elif isinstance(m, nn.GroupNorm):
+                    P[i] = dict(g=m.weight.float().contiguous(), b=m.bias.float().contiguous())
+                elif isinstance(m, nn.Conv2d) and i > 3:     # pyramid conv C -> 4
+                    b16 = torch.zeros(16, device=dev)
+                    b16[:m.bias.shape[0]] = m.bias.float()
+                    P[i] = dict(w=ops.pack_conv_weight([(m.weight.float(), 9)], 16), b=b16)
+            P["conv_in_w"] = self.all_modules[3].weight.float().contiguous()
+            P["conv_in_b"] = self.all_modules[3].bias.float().contiguous()
+            P["Wf"] = self.all_modules[0].W.float().contiguous()
+            P["l1w"], P["l1b"] = self.all_modules[1].weight.float().contiguous(), self.all_modules[1].bias.float().contiguous()
+            P["l2w"], P["l2b"] = self.all_modules[2].weight.float().contiguous(), self.all_modules[2].bias.float().contiguous()
+            wo = self.output_layer.weight.float().reshape(2, 4).cpu().contiguous()
+            P["w_out8"] = (ctypes.c_float * 8)(*wo.flatten().tolist())
+        self._prepared = P
+        return P
+
+    def _skip_weight(self, e, seg_channels, cout):
+        """packed [Npad, 9*cout + sum(seg)] weight of conv1 + 1x1 skip over the given source split"""
+        key = tuple(seg_channels)
+        wp = e["w1_cache"].get(key)
+        if wp is None:
+            segs = [(e["w1_conv"], 9)]
+            c0 = 0
+            for c in seg_channels:
+                segs.append((e["w2_full"][:, c0:c0 + c].contiguous(), 1))
+                c0 += c
+            assert c0 == e["w2_full"].shape[1]
+            wp = ops.pack_conv_weight(segs, self._npad(cout))
+            e["w1_cache"][key] = wp
+        return wp
+
+    # ------------------------------------------------------------------ time embedding
+    def temb_biases(self, t):
+        """Per-res-block conv0 bias vectors b0 + Dense_0(SiLU(temb(t))) (ncsnpp.py:263-274,
+        layerspp.py:270-272).  temb has batch 1 at inference (scalar t) -> depends only on t."""
+        key = float(t)
+        hit = self._temb_cache.get(key)
+        if hit is not None:
+            return hit
+        P = self.prepare()
+        dev = P["Wf"].device
+        nf = self.nf
+        four = torch.empty(2 * nf, device=dev)
+        h1 = torch.empty(4 * nf, device=dev)
+        temb = torch.empty(4 * nf, device=dev)
+        ops.fourier_embed(key, P["Wf"], four)
+        ops.matvec(four, P["l1w"], P["l1b"], h1)
+        ops.matvec(h1, P["l2w"], P["l2b"], temb, silu_in=True)
+        out = {}
+        for i, m in enumerate(self.all_modules):
+            if isinstance(m, ResnetBlockBigGANpp):
+                e = P[i]
+                npad = self._npad(m.out_ch)
+                b = torch.zeros(npad, device=dev)
+                ops.matvec(temb, e["dw"], e["db"], b, silu_in=True, add=e["b0"])
+                out[i] = b
+        self._temb_cache[key] = out
+        return out
+
+    # ------------------------------------------------------------------ building blocks
+    def _partials(self, x, cache):
+        k = x.data_ptr()
+        p = cache.get(k)
+        if p is None:
+            B = x.shape[0]
+            self._stat_counter += 1
+            p = self._ws.get(f"stats{self._stat_counter}", (B, self.stats_slabs, x.shape[3], 2),
+                             torch.float32, x.device)
+            ops.chan_stats(x, self.stats_slabs, out=p)
+            cache[k] = p
+        return p
+
+    def _gn_act(self, srcs, gamma, beta, mode, scache, name):
+        """a = FIR?(SiLU(GroupNorm(cat(srcs)))) as one bf16 NHWC tensor."""
+        B, H, W = srcs[0].shape[:3]
+        C = sum(s.shape[3] for s in srcs)
+        parts = [self._partials(s, scache) for s in srcs]
+        ss = self._ws.get("gn_ss", (B, C, 2), torch.float32, srcs[0].device)
+        ops.gn_finalize(parts, [s.shape[3] for s in srcs], H * W, gamma, beta, min(C // 4, 32), 1e-6, ss)
+        Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
+        a = self._ws.get(name, (B, Ho, Wo, C), torch.bfloat16, srcs[0].device)
+        ops.gn_act_resample(srcs, ss, a, mode, True)
+        return a
+
+    def _resblock(self, i, srcs, tb, scache):
+        """reference layerspp.py:252-284; srcs = virtual concat of bf16 NHWC tensors."""
+        m = self.all_modules[i]
+        e = self._prepared[i]
+        dev = srcs[0].device
+        B, H, W = srcs[0].shape[:3]
+        mode = 1 if m.down else (2 if m.up else 0)
+        Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
+        cin, cout = m.in_ch, m.out_ch
+        assert sum(s.shape[3] for s in srcs) == cin
+        a0 = self._gn_act(srcs, e["g0"], e["be0"], mode, scache, "act")
+        h1 = self._ws.get("h1", (B, Ho, Wo, cout), torch.bfloat16, dev)
+        ops.conv_igemm([(a0, 0, cin, 9)], e["w0"], tb[i], h1, self.max_ctas)
+        scache.pop(h1.data_ptr(), None)
+        a1 = self._gn_act([h1], e["g1"], e["be1"], 0, scache, "act")
+        scache.pop(h1.data_ptr(), None)
+        if mode != 0:
+            xr = self._ws.get("xr", (B, Ho, Wo, cin), torch.bfloat16, dev)
+            ops.gn_act_resample(srcs, None, xr, mode, False)
+            skip = [xr]
+        else:
+            skip = list(srcs)
+        wp = self._skip_weight(e, [s.shape[3] for s in skip], cout)
+        out = self._ws.get(f"rb{i}", (B, Ho, Wo, cout), torch.bfloat16, dev)
+        ops.conv_igemm([(a1, 0, cout, 9)] + [(s, 0, s.shape[3], 1) for s in skip], wp, e["b1"], out,
+                       self.max_ctas)
+        scache.pop(out.data_ptr(), None)
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def velocity(self, x, y, t, out=None, base1=None, c1=0.0, base2=None, c2=0.0, coef=1.0, v_out=None):
+        """v = backbone(x, y, t) with the ODE stage fused into the last kernel:
+        out = c1*base1 + c2*base2 + coef*v.  x, y, bases, out: fp32 [B,F,T,2] (= complex64 [B,F,T])."""
+        P = self.prepare()
+        tb = self.temb_biases(t)
+        ws, dev = self._ws, x.device
+        B, Fq, T = x.shape[0], x.shape[1], x.shape[2]
+        nres = self.num_resolutions
+        if Fq % (16 << (nres - 1)) or T % (8 << (nres - 1)):
+            raise ValueError(f"spectrogram {Fq}x{T} is not tileable for {nres} resolutions "
+                             "(need F % (16*2^(L-1)) == 0 and T % (8*2^(L-1)) == 0; pad_spec pads T to 64)")
+        scache = {}
+        self._stat_counter = 0
+        mods = self.all_modules
+        pyr_in = ops.pack4(x, y, ws.get("pyr_in0", (B, Fq, T, 4), torch.float32, dev))
+        h = ops.conv_in(pyr_in, P["conv_in_w"], P["conv_in_b"], ws.get("h_in", (B, Fq, T, self.nf), torch.bfloat16, dev))
+        hs = [h]
+        idx = 4
+        H, W = Fq, T
+        for lvl in range(nres):
+            for _ in range(self.num_res_blocks):
+                hs.append(self._resblock(idx, [hs[-1]], tb, scache))
+                idx += 1
+            if lvl != nres - 1:
+                hd = self._resblock(idx, [hs[-1]], tb, scache)
+                idx += 1
+                H, W = H // 2, W // 2
+                pyr_in = ops.fir_down4(pyr_in, ws.get(f"pyr_in{lvl + 1}", (B, H, W, 4), torch.float32, dev))
+                c = P[idx]
+                hc = ops.combine(pyr_in, c["w"], c["b"], hd, ws.get(f"comb{idx}", hd.shape, torch.bfloat16, dev))
+                scache.pop(hc.data_ptr(), None)
+                idx += 1
+                hs.append(hc)
+        h = hs[-1]
+        h = self._resblock(idx, [h], tb, scache)
+        idx += 1
+        h = self._resblock(idx, [h], tb, scache)
+        idx += 1
+        pyramid = None
+        for lvl in reversed(range(nres)):
+            for _ in range(self.num_res_blocks + 1):
+                h = self._resblock(idx, [h, hs.pop()], tb, scache)
+                idx += 1
+            g = P[idx]
+            a = self._gn_act([h], g["g"], g["b"], 0, scache, "act")
+            idx += 1
+            pc = P[idx]
+            ph = ws.get(f"pyr_out{lvl}", (B, H, W, 4), torch.float32, dev)
+            ops.conv_igemm([(a, 0, a.shape[3], 9)], pc["w"], pc["b"], ph, self.max_ctas)
+            idx += 1
+            pyramid = ph if pyramid is None else ops.pyramid_up_add(pyramid, ph, ph)
+            if lvl != 0:
+                h = self._resblock(idx, [h], tb, scache)
+                idx += 1
+                H, W = H * 2, W * 2
+        assert not hs and idx == len(mods)
+        if out is None and v_out is None:
+            v_out = torch.empty(B, Fq, T, 2, device=dev, dtype=torch.float32)
+        ops.output_axpy(pyramid, P["w_out8"], base1, c1, base2, c2, coef, out, v_out)
+        return out if out is not None else v_out
+
+    def forward(self, x, y, t):
+        """x, y: complex64 [B,1,F,T]; t: float tensor with one element (the reference passes a
+        shared scalar time, model.py:470-474).  Returns complex64 [B,1,F,T]."""
+        if torch.is_tensor(t):
+            if t.numel() != 1 and not bool((t == t.flatten()[0]).all()):
+                raise NotImplementedError("per-sample t is not supported (FlowDec inference uses a shared t)")
+            t = float(t.flatten()[0])
+        xr = torch.view_as_real(x.to(torch.complex64).contiguous()).squeeze(1).contiguous()
+        yr = torch.view_as_real(y.to(torch.complex64).contiguous()).squeeze(1).contiguous()
+        v = torch.empty_like(xr)
+        self.velocity(xr, yr, t, v_out=v)
+        return torch.view_as_complex(v).unsqueeze(1)

@@ -16,7 +16,6 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
-    "--use_fast_math",
     "-Xptxas", "-v",
 ]
 

@@ -1,0 +1,568 @@
+// flowdec_b200 — HBM-bound kernels around the tcgen05 convolutions of the NCSN++ backbone.
+//
+//   GroupNorm statistics / affine+SiLU (+FIR x2 up/down)   reference layerspp.py:252-268,
+//                                                          up_or_down_sampling.py:220-282,
+//                                                          op/upfirdn2d_kernel.cu:118-218
+//   4->64 input conv, Combine 1x1, 4-channel pyramids      reference ncsnpp.py:284,300-321,355-384
+//   output 1x1 conv fused with the ODE update              reference ncsnpp.py:398 + torchdyn step
+//   time embedding + per-block Dense_0 bias                reference ncsnpp.py:263-274, layerspp.py:270-272
+//
+// Layouts: activations bf16 NHWC [B,H,W,C]; 4-channel pyramids fp32 [B,H,W,4]; ODE state and
+// spectrograms float2 [B,F,T] (bit-identical to complex64 [B,1,F,T]).
+#include "fd_common.cuh"
+
+namespace fd {
+
+// FIR taps of the separable [1,3,3,1] filter (normalised per axis)
+// down (factor 2, pad (1,1)):  out[i]   = (x[2i-1] + 3 x[2i] + 3 x[2i+1] + x[2i+2]) / 8
+// up   (factor 2, pad (2,1)):  out[2i]  = (x[i-1] + 3 x[i]) / 4 ; out[2i+1] = (3 x[i] + x[i+1]) / 4
+
+struct bf16x8 {
+  uint4 raw;
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 r;
+  r.x = pack_bf16x2(v[0], v[1]);
+  r.y = pack_bf16x2(v[2], v[3]);
+  r.z = pack_bf16x2(v[4], v[5]);
+  r.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-(sample, channel) sum / sum-of-squares, deterministic two-level reduction
+//   partial[b][s][c][2]  (fp32), s = slab index; finalize reduces slabs in fp64
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chan_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW,
+                                                         int C, float* __restrict__ partial, int S) {
+  extern __shared__ float red[];  // [256][16]
+  const int b = blockIdx.y, s = blockIdx.x;
+  const int oct = C >> 3;                 // threads per pixel
+  const int ppi = 256 / oct;              // pixels per iteration
+  const int o = threadIdx.x % oct;
+  const int pl = threadIdx.x / oct;
+  const int per = (HW + S - 1) / S;
+  const int p0 = s * per;
+  const int p1 = min(HW, p0 + per);
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+  const __nv_bfloat16* base = x + static_cast<size_t>(b) * HW * C + o * 8;
+  if (pl < ppi) {
+    for (int p = p0 + pl; p < p1; p += ppi) {
+      float v[8];
+      load8(base + static_cast<size_t>(p) * C, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sum[i] += v[i];
+        sq[i] = fmaf(v[i], v[i], sq[i]);
+      }
+    }
+  }
+  float* my = red + threadIdx.x * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    my[i] = sum[i];
+    my[8 + i] = sq[i];
+  }
+  __syncthreads();
+  // thread t < C*2 reduces one (channel, stat) over the ppi pixel lanes, fixed order
+  for (int t = threadIdx.x; t < C * 2; t += 256) {
+    const int c = t >> 1, st = t & 1;
+    const int oo = c >> 3, ci = c & 7;
+    float acc = 0.f;
+    for (int q = 0; q < ppi; ++q) acc += red[(q * oct + oo) * 16 + st * 8 + ci];
+    partial[((static_cast<size_t>(b) * S + s) * C + c) * 2 + st] = acc;
+  }
+}
+
+// one block per (group, sample): mean / rstd over the group's channels of the virtual concat
+// [src1 (C1 channels), src2 (C2 channels)], then per-channel scale/shift.
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part1, int C1,
+                                                          const float* __restrict__ part2, int C2,
+                                                          int S, double count,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, int groups,
+                                                          float eps, float* __restrict__ scale_shift) {
+  __shared__ double ssum[128], ssq[128];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int C = C1 + C2;
+  const int cpg = C / groups;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < cpg * S; i += 128) {
+    const int c = g * cpg + i / S;
+    const int sl = i % S;
+    const float* p = (c < C1) ? part1 + ((static_cast<size_t>(b) * S + sl) * C1 + c) * 2
+                              : part2 + ((static_cast<size_t>(b) * S + sl) * C2 + (c - C1)) * 2;
+    s += static_cast<double>(p[0]);
+    q += static_cast<double>(p[1]);
+  }
+  ssum[threadIdx.x] = s;
+  ssq[threadIdx.x] = q;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      ssum[threadIdx.x] += ssum[threadIdx.x + off];
+      ssq[threadIdx.x] += ssq[threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  const double n = count * cpg;
+  const double mean = ssum[0] / n;
+  double var = ssq[0] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
+  for (int i = threadIdx.x; i < cpg; i += 128) {
+    const int c = g * cpg + i;
+    const double sc = static_cast<double>(gamma[c]) * rstd;
+    scale_shift[(static_cast<size_t>(b) * C + c) * 2 + 0] = static_cast<float>(sc);
+    scale_shift[(static_cast<size_t>(b) * C + c) * 2 + 1] =
+        static_cast<float>(static_cast<double>(beta[c]) - mean * sc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a = [FIR](SiLU(x * scale + shift)) over the virtual concat [src1, src2] -> bf16 NHWC.
+// MODE 0: same resolution, 1: FIR down x2, 2: FIR up x2.  ACT=false: raw FIR of x (skip path).
+// One thread per (output pixel, 8 channels).
+// ------------------------------------------------------------------------------------------
+template <int MODE, bool ACT>
+__global__ void __launch_bounds__(256) gn_act_resample_kernel(
+    const __nv_bfloat16* __restrict__ src1, int C1, const __nv_bfloat16* __restrict__ src2, int C2,
+    const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  const int C = C1 + C2;
+  const int oct = C >> 3;
+  const int Ho = (MODE == 1) ? H / 2 : (MODE == 2 ? H * 2 : H);
+  const int Wo = (MODE == 1) ? W / 2 : (MODE == 2 ? W * 2 : W);
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * oct;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(idx % oct);
+    size_t pix = idx / oct;
+    const int wo = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int ho = static_cast<int>(pix % Ho);
+    const int b = static_cast<int>(pix / Ho);
+    const int c0 = o * 8;
+    const __nv_bfloat16* src;
+    int Cs, cs;
+    if (c0 < C1) {
+      src = src1; Cs = C1; cs = c0;
+    } else {
+      src = src2; Cs = C2; cs = c0 - C1;
+    }
+    float sc[8], sh[8];
+    if (ACT) {
+      const float4* ss = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(b) * C + c0) * 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = ss[i];
+        sc[2 * i] = t.x; sh[2 * i] = t.y; sc[2 * i + 1] = t.z; sh[2 * i + 1] = t.w;
+      }
+    }
+    const __nv_bfloat16* img = src + static_cast<size_t>(b) * H * W * Cs + cs;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+    auto tap = [&](int hi, int wi, float wgt) {
+      if (hi < 0 || hi >= H || wi < 0 || wi >= W) return;
+      float v[8];
+      load8(img + (static_cast<size_t>(hi) * W + wi) * Cs, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = v[i];
+        if (ACT) a = silu_f(fmaf(a, sc[i], sh[i]));
+        acc[i] = fmaf(wgt, a, acc[i]);
+      }
+    };
+
+    if (MODE == 0) {
+      tap(ho, wo, 1.0f);
+    } else if (MODE == 1) {
+      const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) tap(2 * ho - 1 + a, 2 * wo - 1 + bb, k[a] * k[bb]);
+    } else {
+      const int hi = ho >> 1, wi = wo >> 1;
+      const int hn = (ho & 1) ? hi + 1 : hi - 1;  // the 1/4-weight neighbour
+      const int wn = (wo & 1) ? wi + 1 : wi - 1;
+      tap(hi, wi, 0.5625f);
+      tap(hi, wn, 0.1875f);
+      tap(hn, wi, 0.1875f);
+      tap(hn, wn, 0.0625f);
+    }
+    store8(out + ((static_cast<size_t>(b) * Ho + ho) * Wo + wo) * C + c0, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 4-channel fp32 helpers
+// ------------------------------------------------------------------------------------------
+__global__ void pack4_kernel(const float2* __restrict__ x, const float2* __restrict__ y,
+                             float4* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float2 a = x[i], b = y[i];
+    out[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
+__global__ void fir_down4_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int H,
+                                 int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo;
+  const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int wo = static_cast<int>(idx % Wo);
+    const int ho = static_cast<int>((idx / Wo) % Ho);
+    const int b = static_cast<int>(idx / (static_cast<size_t>(Wo) * Ho));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int hi = 2 * ho - 1 + a;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const int wi = 2 * wo - 1 + bb;
+        if (wi < 0 || wi >= W) continue;
+        const float4 v = in[(static_cast<size_t>(b) * H + hi) * W + wi];
+        const float wgt = k[a] * k[bb];
+        acc.x = fmaf(wgt, v.x, acc.x);
+        acc.y = fmaf(wgt, v.y, acc.y);
+        acc.z = fmaf(wgt, v.z, acc.z);
+        acc.w = fmaf(wgt, v.w, acc.w);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+// out[2H,2W] = FIR_up(lo[H,W]) + add[2H,2W]   (out may alias add)
+__global__ void pyramid_up_add_kernel(const float4* __restrict__ lo, const float4* add,
+                                      float4* out, int B, int H, int W) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int wo = static_cast<int>(idx % Wo);
+    const int ho = static_cast<int>((idx / Wo) % Ho);
+    const int b = static_cast<int>(idx / (static_cast<size_t>(Wo) * Ho));
+    const int hi = ho >> 1, wi = wo >> 1;
+    const int hn = (ho & 1) ? hi + 1 : hi - 1;
+    const int wn = (wo & 1) ? wi + 1 : wi - 1;
+    float4 acc = add[idx];
+    auto tap = [&](int h, int w, float wgt) {
+      if (h < 0 || h >= H || w < 0 || w >= W) return;
+      const float4 v = lo[(static_cast<size_t>(b) * H + h) * W + w];
+      acc.x = fmaf(wgt, v.x, acc.x);
+      acc.y = fmaf(wgt, v.y, acc.y);
+      acc.z = fmaf(wgt, v.z, acc.z);
+      acc.w = fmaf(wgt, v.w, acc.w);
+    };
+    tap(hi, wi, 0.5625f);
+    tap(hi, wn, 0.1875f);
+    tap(hn, wi, 0.1875f);
+    tap(hn, wn, 0.0625f);
+    out[idx] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// input conv 3x3, 4 -> 64 channels (fp32 math on CUDA cores, K = 36 is too thin for UMMA)
+// block = 32 pixels (along W) x 8 channel-octets; weights [64][4][3][3] staged in smem as
+// [tap*4+ci][64]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_in_kernel(const float4* __restrict__ in,
+                                                      const float* __restrict__ w,
+                                                      const float* __restrict__ bias,
+                                                      __nv_bfloat16* __restrict__ out, int B, int H,
+                                                      int W) {
+  __shared__ float sw[36][64];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 64 * 36; i += 256) {
+    const int co = i / 36, r = i % 36;      // r = ci*9 + kh*3 + kw   (OIHW)
+    const int ci = r / 9, t = r % 9;
+    sw[t * 4 + ci][co] = w[i];
+  }
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, o = threadIdx.x >> 5;
+  const int wtiles = (W + 31) / 32;
+  const size_t ntiles = static_cast<size_t>(B) * H * wtiles;
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int wt = static_cast<int>(tile % wtiles);
+    const int h = static_cast<int>((tile / wtiles) % H);
+    const int b = static_cast<int>(tile / (static_cast<size_t>(wtiles) * H));
+    const int wx = wt * 32 + lane;
+    if (wx >= W) continue;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = sb[o * 8 + i];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = h + kh - 1;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wx + kw - 1;
+        if (wi < 0 || wi >= W) continue;
+        const float4 v = in[(static_cast<size_t>(b) * H + hi) * W + wi];
+        const int t = kh * 3 + kw;
+        const float* w0 = &sw[t * 4 + 0][o * 8];
+        const float* w1 = &sw[t * 4 + 1][o * 8];
+        const float* w2 = &sw[t * 4 + 2][o * 8];
+        const float* w3 = &sw[t * 4 + 3][o * 8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] = fmaf(v.x, w0[i], acc[i]);
+          acc[i] = fmaf(v.y, w1[i], acc[i]);
+          acc[i] = fmaf(v.z, w2[i], acc[i]);
+          acc[i] = fmaf(v.w, w3[i], acc[i]);
+        }
+      }
+    }
+    store8(out + ((static_cast<size_t>(b) * H + h) * W + wx) * 64 + o * 8, acc);
+  }
+}
+
+// Combine(method='sum'): out = h + Conv1x1_{4->C}(pyr) + bias   (layerspp.py:62-69)
+__global__ void __launch_bounds__(256) combine_kernel(const float4* __restrict__ pyr,
+                                                      const float* __restrict__ w,   // [C][4]
+                                                      const float* __restrict__ bias,
+                                                      const __nv_bfloat16* __restrict__ h,
+                                                      __nv_bfloat16* __restrict__ out, size_t npix,
+                                                      int C) {
+  const int oct = C >> 3;
+  const size_t total = npix * oct;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(idx % oct);
+    const size_t pix = idx / oct;
+    const float4 p = pyr[pix];
+    float v[8];
+    load8(h + pix * C + o * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = o * 8 + i;
+      const float4 wc = *reinterpret_cast<const float4*>(w + c * 4);
+      v[i] += bias[c] + wc.x * p.x + wc.y * p.y + wc.z * p.z + wc.w * p.w;
+    }
+    store8(out + pix * C + o * 8, v);
+  }
+}
+
+// v = W_out[2x4] * pyr ; out = c1*base1 + c2*base2 + coef*v   (complex as float2; fused ODE stage)
+__global__ void output_axpy_kernel(const float4* __restrict__ pyr, float w00, float w01, float w02,
+                                   float w03, float w10, float w11, float w12, float w13,
+                                   const float2* __restrict__ base1, float c1,
+                                   const float2* __restrict__ base2, float c2, float coef,
+                                   float2* __restrict__ out, float2* __restrict__ v_out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 p = pyr[i];
+    const float vr = w00 * p.x + w01 * p.y + w02 * p.z + w03 * p.w;
+    const float vi = w10 * p.x + w11 * p.y + w12 * p.z + w13 * p.w;
+    if (v_out) v_out[i] = make_float2(vr, vi);
+    if (out) {
+      float2 r = make_float2(coef * vr, coef * vi);
+      if (base1) {
+        const float2 a = base1[i];
+        r.x = fmaf(c1, a.x, r.x);
+        r.y = fmaf(c1, a.y, r.y);
+      }
+      if (base2) {
+        const float2 a = base2[i];
+        r.x = fmaf(c2, a.x, r.x);
+        r.y = fmaf(c2, a.y, r.y);
+      }
+      out[i] = r;
+    }
+  }
+}
+
+// x0 = Y + fac * (float)(sigma[f] (f64) * eps)      (model.py:512,530-536)
+__global__ void x0_kernel(const float2* __restrict__ Y, const double* __restrict__ sigma,
+                          const float2* __restrict__ eps, float fac, float2* __restrict__ out, int Fq,
+                          int T, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int f = static_cast<int>((i / T) % Fq);
+    const double s = sigma[f];
+    const float2 e = eps[i], y = Y[i];
+    const float nr = static_cast<float>(s * static_cast<double>(e.x));
+    const float ni = static_cast<float>(s * static_cast<double>(e.y));
+    out[i] = make_float2(y.x + fac * nr, y.y + fac * ni);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// time embedding (tiny; fp64 trig because 2*pi*t*W reaches hundreds of radians)
+// ------------------------------------------------------------------------------------------
+__global__ void fourier_embed_kernel(float t, const float* __restrict__ Wf, int nf,
+                                     float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nf) {
+    // reference computes x[:,None] * W[None,:] * 2 * np.pi in fp32 (layerspp.py:50)
+    const float proj = t * Wf[i] * 2.0f * 3.14159265358979323846f;
+    out[i] = static_cast<float>(sin(static_cast<double>(proj)));
+    out[nf + i] = static_cast<float>(cos(static_cast<double>(proj)));
+  }
+}
+
+// out[m] = (add ? add[m] : 0) + out_scale * (b[m] + sum_k W[m][k] * act(in[k]));  one warp per row
+__global__ void matvec_kernel(const float* __restrict__ in, int K, int silu_in,
+                              const float* __restrict__ Wm, const float* __restrict__ b,
+                              const float* __restrict__ add, float out_scale,
+                              float* __restrict__ out, int M) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float v = in[k];
+    if (silu_in) v = v / (1.0f + expf(-v));
+    acc = fmaf(Wm[static_cast<size_t>(row) * K + k], v, acc);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) out[row] = (add ? add[row] : 0.f) + out_scale * (acc + (b ? b[row] : 0.f));
+}
+
+static inline int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = static_cast<size_t>(148) * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace fd
+
+using namespace fd;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int fd_chan_stats(const void* x, int B, int HW, int C, float* partial, int S,
+                             cudaStream_t stream) {
+  FD_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, "fd_chan_stats: unsupported C=%d", C);
+  FD_REQUIRE(S >= 1, "fd_chan_stats: S must be >= 1");
+  chan_stats_kernel<<<dim3(S, B), 256, 256 * 16 * sizeof(float), stream>>>(
+      static_cast<const bf16*>(x), HW, C, partial, S);
+  return check_launch("fd_chan_stats");
+}
+
+extern "C" int fd_gn_finalize(const float* part1, int C1, const float* part2, int C2, int S, int B,
+                              double count, const float* gamma, const float* beta, int groups,
+                              float eps, float* scale_shift, cudaStream_t stream) {
+  FD_REQUIRE((C1 + C2) % groups == 0, "fd_gn_finalize: C=%d not divisible by groups=%d", C1 + C2, groups);
+  gn_finalize_kernel<<<dim3(groups, B), 128, 0, stream>>>(part1, C1, part2, C2, S, count, gamma, beta,
+                                                          groups, eps, scale_shift);
+  return check_launch("fd_gn_finalize");
+}
+
+extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, int C2,
+                                  const float* scale_shift, void* out, int B, int H, int W, int mode,
+                                  int apply_act, cudaStream_t stream) {
+  FD_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0, "fd_gn_act_resample: channels must be multiples of 8");
+  FD_REQUIRE(mode >= 0 && mode <= 2, "fd_gn_act_resample: mode %d", mode);
+  FD_REQUIRE(mode != 1 || (H % 2 == 0 && W % 2 == 0), "fd_gn_act_resample: odd size for down-sampling");
+  const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H);
+  const int Wo = mode == 1 ? W / 2 : (mode == 2 ? W * 2 : W);
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * ((C1 + C2) / 8);
+  const int grid = grid_for(total, 256);
+  const bf16* s1 = static_cast<const bf16*>(src1);
+  const bf16* s2 = static_cast<const bf16*>(src2);
+  bf16* o = static_cast<bf16*>(out);
+#define FD_LAUNCH_GN(M, A) \
+  gn_act_resample_kernel<M, A><<<grid, 256, 0, stream>>>(s1, C1, s2, C2, scale_shift, o, B, H, W)
+  if (apply_act) {
+    if (mode == 0) FD_LAUNCH_GN(0, true);
+    else if (mode == 1) FD_LAUNCH_GN(1, true);
+    else FD_LAUNCH_GN(2, true);
+  } else {
+    if (mode == 0) FD_LAUNCH_GN(0, false);
+    else if (mode == 1) FD_LAUNCH_GN(1, false);
+    else FD_LAUNCH_GN(2, false);
+  }
+#undef FD_LAUNCH_GN
+  return check_launch("fd_gn_act_resample");
+}
+
+extern "C" int fd_pack4(const void* x, const void* y, void* out, size_t npix, cudaStream_t stream) {
+  pack4_kernel<<<grid_for(npix, 256), 256, 0, stream>>>(static_cast<const float2*>(x),
+                                                       static_cast<const float2*>(y),
+                                                       static_cast<float4*>(out), npix);
+  return check_launch("fd_pack4");
+}
+
+extern "C" int fd_fir_down4(const void* in, void* out, int B, int H, int W, cudaStream_t stream) {
+  FD_REQUIRE(H % 2 == 0 && W % 2 == 0, "fd_fir_down4: odd size");
+  fir_down4_kernel<<<grid_for(static_cast<size_t>(B) * (H / 2) * (W / 2), 256), 256, 0, stream>>>(
+      static_cast<const float4*>(in), static_cast<float4*>(out), B, H, W);
+  return check_launch("fd_fir_down4");
+}
+
+extern "C" int fd_pyramid_up_add(const void* lo, const void* add, void* out, int B, int H, int W,
+                                 cudaStream_t stream) {
+  pyramid_up_add_kernel<<<grid_for(static_cast<size_t>(B) * H * W * 4, 256), 256, 0, stream>>>(
+      static_cast<const float4*>(lo), static_cast<const float4*>(add), static_cast<float4*>(out), B, H,
+      W);
+  return check_launch("fd_pyramid_up_add");
+}
+
+extern "C" int fd_conv_in(const void* in4, const float* w, const float* bias, void* out, int B, int H,
+                          int W, cudaStream_t stream) {
+  const size_t ntiles = static_cast<size_t>(B) * H * ((W + 31) / 32);
+  const int grid = static_cast<int>(ntiles < 148 * 8 ? ntiles : 148 * 8);
+  conv_in_kernel<<<grid, 256, 0, stream>>>(static_cast<const float4*>(in4), w, bias,
+                                           static_cast<bf16*>(out), B, H, W);
+  return check_launch("fd_conv_in");
+}
+
+extern "C" int fd_combine(const void* pyr4, const float* w, const float* bias, const void* h, void* out,
+                          size_t npix, int C, cudaStream_t stream) {
+  FD_REQUIRE(C % 8 == 0, "fd_combine: C=%d", C);
+  combine_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, stream>>>(
+      static_cast<const float4*>(pyr4), w, bias, static_cast<const bf16*>(h), static_cast<bf16*>(out),
+      npix, C);
+  return check_launch("fd_combine");
+}
+
+extern "C" int fd_output_axpy(const void* pyr4, const float* w_out_host8, const void* base1, float c1,
+                              const void* base2, float c2, float coef, void* out, void* v_out,
+                              size_t npix, cudaStream_t stream) {
+  const float* w = w_out_host8;  // host pointer: 2x4 weights, passed by value into the launch
+  output_axpy_kernel<<<grid_for(npix, 256), 256, 0, stream>>>(
+      static_cast<const float4*>(pyr4), w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7],
+      static_cast<const float2*>(base1), c1, static_cast<const float2*>(base2), c2, coef,
+      static_cast<float2*>(out), static_cast<float2*>(v_out), npix);
+  return check_launch("fd_output_axpy");
+}
+
+extern "C" int fd_x0(const void* Y, const double* sigma, const void* eps, float fac, void* out, int B,
+                     int Fq, int T, cudaStream_t stream) {
+  const size_t n = static_cast<size_t>(B) * Fq * T;
+  x0_kernel<<<grid_for(n, 256), 256, 0, stream>>>(static_cast<const float2*>(Y), sigma,
+                                                  static_cast<const float2*>(eps), fac,
+                                                  static_cast<float2*>(out), Fq, T, n);
+  return check_launch("fd_x0");
+}
+
+extern "C" int fd_fourier_embed(float t, const float* Wf, int nf, float* out, cudaStream_t stream) {
+  fourier_embed_kernel<<<(nf + 127) / 128, 128, 0, stream>>>(t, Wf, nf, out);
+  return check_launch("fd_fourier_embed");
+}
+
+extern "C" int fd_matvec(const float* in, int K, int silu_in, const float* Wm, const float* b,
+                         const float* add, float out_scale, float* out, int M, cudaStream_t stream) {
+  matvec_kernel<<<(M + 7) / 8, 256, 0, stream>>>(in, K, silu_in, Wm, b, add, out_scale, out, M);
+  return check_launch("fd_matvec");
+}

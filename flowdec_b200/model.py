@@ -1,0 +1,230 @@
+"""FlowDec enhancement model API on B200.
+
+Mirror of /root/reference/flowdec/model.py `EnhancementModel` / `FlowModel` for the inference
+half: constructor keywords, `enhance()` signature and return conventions,
+`forward(xt, y, t)`, `_preprocess/_postprocess`, `.device`, `.sampling_rate`, and the 265
+state_dict keys.  No lightning / hydra / torchdyn / torchcfm dependency: the ODE loop
+(torchdyn.NeuralODE.trajectory in the reference, model.py:511-514) is a host-side schedule of
+fused kernel launches (flowdec_b200/sampling/solvers.py), optionally captured as one CUDA graph
+per (batch, length, N, solver).
+"""
+import warnings
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .sampling.solvers import get_solver, nfe_per_step, stages, t_grid
+from .util.other import padded_frames
+
+
+class EnhancementModel(nn.Module):
+    """inference-only stand-in for the reference's LightningModule base (model.py:37-190)"""
+
+    strict_loading = False
+
+    def __init__(self, backbone: nn.Module, feature_extractor, sampling_rate: int, lr: float = 1e-4,
+                 normalize_mode: str = "noisy", optimizer_init=None, datamodule=None, eval_metrics=None,
+                 eval_variants=None, num_eval_files: int = 20, full_config: Optional[dict] = None,
+                 evaluation_seed: Optional[int] = None):
+        super().__init__()
+        self.sampling_rate = sampling_rate
+        self.normalize_mode = normalize_mode
+        assert self.normalize_mode in ("noisy", "none")
+        self.lr = lr
+        self.backbone = backbone
+        self.feature_extractor = feature_extractor
+        self.full_config = full_config
+        self.hparams = full_config
+        self.eval_metrics, self.eval_variants = eval_metrics, eval_variants
+        self.num_eval_files, self.evaluation_seed = num_eval_files, evaluation_seed
+        self.datamodule, self.optimizer_init = datamodule, optimizer_init
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, ema=True, build_fn=None, **kwargs):
+        """What the reference intends (model.py:352-385, commented out there): build the model, then
+        load `_pl_ema_state_dict` (ema=True) or `state_dict`.  Hydra is not a dependency here, so the
+        model comes from `build_fn()` (default: the shipped flowdec_75m configuration)."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        model = build_fn() if build_fn is not None else build_flowdec("75m")
+        sd = ckpt["_pl_ema_state_dict"] if ema else ckpt["state_dict"]
+        model.load_state_dict(sd, strict=False)
+        return model
+
+
+class FlowModel(EnhancementModel):
+    """Flow-matching postfilter (reference model.py:391-536), inference path."""
+
+    def __init__(self, flow_matcher, sigma_x, sigma_y, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.flow_matcher = flow_matcher
+        as_t = lambda v: v if isinstance(v, torch.Tensor) else torch.tensor(float(v))
+        if callable(sigma_x) or callable(sigma_y):
+            raise NotImplementedError("callable sigma_x / sigma_y (reference model.py:407-419) is a training-time option")
+        self.sigma_x = nn.Parameter(as_t(sigma_x), requires_grad=False)
+        self.sigma_y = nn.Parameter(as_t(sigma_y), requires_grad=False)
+        self._graphs = {}
+        self.use_cuda_graph = True
+        self.max_batch = 8          # clips per backbone pass (micro-batch)
+        self._sig_cache = None
+
+    def _apply(self, fn, *a, **k):
+        self._graphs = {}
+        self._sig_cache = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict=None, **kw):
+        self._graphs = {}
+        self._sig_cache = None
+        return super().load_state_dict(state_dict, strict=self.strict_loading if strict is None else strict, **kw)
+
+    # ------------------------------------------------------------------------------------
+    def forward(self, xt, y, t):
+        if torch.is_tensor(t) and t.ndim == 0:
+            t = t.unsqueeze(0)
+        return self.backbone(xt, y, t)
+
+    def _sigma_vec(self, Fq):
+        if self._sig_cache is None:
+            s = self.sigma_y.detach().to(torch.float64).reshape(-1)
+            if s.numel() == 1:
+                s = s.expand(Fq)
+            self._sig_cache = s.contiguous()
+        if self._sig_cache.numel() != Fq:
+            raise ValueError(f"sigma_y has {self._sig_cache.numel()} entries, spectrogram has {Fq} bins")
+        return self._sig_cache
+
+    def _get_noise(self, x, sigma):
+        """reference model.py:530-536 (used by enhance unless `noise=` is injected)"""
+        return (sigma * torch.randn_like(x)).type(x.dtype)
+
+    # ------------------------------------------------------------------------------------
+    def _run(self, st, N, solver, sigma_fac, want_traj):
+        """All device work of enhance() on static buffers `st` (graph-capturable)."""
+        fe, bb = self.feature_extractor, self.backbone
+        B, L, Tp = st["B"], st["L"], st["Tp"]
+        ops.normfac(st["y"], 1 if self.normalize_mode == "noisy" else 0, st["nf"])
+        fe.stft_compress(st["y"], st["nf"], st["Y"])
+        ops.x0_noise(st["Y"], self._sigma_vec(768), st["eps"], sigma_fac, st["x"][0])
+        cur = 0
+        traj = [st["x"][0]] if want_traj else None
+        for (t, dt) in t_grid(N):
+            bufs = {"x": st["x"][cur], "xn": st["x"][cur ^ 1], "tmp": st["tmp"]}
+            for (te, src, dst, b1, c1, b2, c2, coef) in stages(solver, t, dt):
+                for lo in range(0, B, self.max_batch):
+                    hi = min(B, lo + self.max_batch)
+                    sl = lambda name: bufs[name][lo:hi] if name is not None else None
+                    bb.velocity(sl(src), st["Y"][lo:hi], float(te), out=sl(dst), base1=sl(b1), c1=c1,
+                                base2=sl(b2), c2=c2, coef=coef)
+            cur ^= 1
+            if want_traj:
+                keep = torch.empty_like(st["x"][cur])
+                keep.copy_(st["x"][cur])
+                traj.append(keep)
+        fe.istft_decompress(st["x"][cur], L, st["nf"], st["out"])
+        return traj
+
+    def _static(self, B, L, dev):
+        Tp = padded_frames(1 + L // 384)
+        f32 = dict(device=dev, dtype=torch.float32)
+        return dict(B=B, L=L, Tp=Tp, y=torch.empty(B, L, **f32), nf=torch.empty(B, **f32),
+                    Y=torch.empty(B, 768, Tp, 2, **f32), eps=torch.empty(B, 768, Tp, 2, **f32),
+                    x=[torch.empty(B, 768, Tp, 2, **f32) for _ in range(2)],
+                    tmp=torch.empty(B, 768, Tp, 2, **f32), out=torch.empty(B, L, **f32))
+
+    @torch.no_grad()
+    def enhance(self, y, return_preprocess_info: bool = False, N: int = 50, solver: str = "euler",
+                with_grad: bool = False, sigma_fac: float = 1.0, return_traj: bool = False,
+                noise: Optional[torch.Tensor] = None, **kwargs):
+        """Enhance a coded waveform `y` ([B,1,L], [1,L] or [L]); reference model.py:476-528.
+
+        Extra keyword `noise`: complex64 [B,1,768,Tp] standing in for torch.randn_like(Y) (parity
+        tests inject the oracle's draw).  Unknown kwargs (predictor/corrector/snr from the
+        reference CLI, enhance.py:55-61) are accepted and ignored like the reference does."""
+        if with_grad:
+            raise NotImplementedError("with_grad=True (backprop through the solver) is a training feature")
+        solver = get_solver(solver)
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("flowdec_b200 runs on CUDA (sm_100a) only; call model.cuda()")
+        squeeze_dims = 0
+        y_in = y
+        while y.ndim < 3:
+            y = y.unsqueeze(0)
+            squeeze_dims += 1
+        B, C, L = y.shape
+        if L <= 767:
+            raise ValueError(f"waveform length {L} must exceed the STFT reflect pad (767)")
+        key = (B * C, L, int(N), solver, float(sigma_fac))
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = dict(st=self._static(B * C, L, dev), graph=None, warm=0)
+            self._graphs[key] = entry
+        st = entry["st"]
+        st["y"].copy_(y.reshape(B * C, L), non_blocking=True)
+        if noise is None:
+            eps = torch.randn(B, C, 768, st["Tp"], dtype=torch.complex64, device=dev)
+        else:
+            eps = noise.to(dev, torch.complex64)
+        st["eps"].copy_(torch.view_as_real(eps.reshape(B * C, 768, st["Tp"])))
+        traj = None
+        if return_traj or not self.use_cuda_graph:
+            traj = self._run(st, N, solver, sigma_fac, return_traj)
+        elif entry["graph"] is None:
+            # first call: eager (also builds packed weights / time-embedding caches); second: capture
+            if entry["warm"] == 0:
+                self._run(st, N, solver, sigma_fac, False)
+                entry["warm"] = 1
+            else:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._run(st, N, solver, sigma_fac, False)
+                entry["graph"] = g
+                g.replay()
+        else:
+            entry["graph"].replay()
+
+        info = dict(orig_length=L, normfac=st["nf"].clone().reshape(B, C, 1) if C == 1 else st["nf"].clone(),
+                    undo_pad_fn=(lambda Y_, T=1 + L // 384: Y_[..., :T]), squeeze_dims=squeeze_dims)
+        if return_traj:
+            fe = self.feature_extractor
+            X_hats, x_hats = [], []
+            for X in traj:
+                w = torch.empty(B * C, L, device=dev, dtype=torch.float32)
+                fe.istft_decompress(X, L, st["nf"], w)
+                X_hats.append(torch.view_as_complex(X.clone()).reshape(B, C, 768, st["Tp"]))
+                xw = w.reshape(B, C, L)
+                for _ in range(squeeze_dims):
+                    xw = xw.squeeze(0)
+                x_hats.append(xw)
+            return torch.stack(X_hats), x_hats
+        x_hat = st["out"].clone().reshape(B, C, L)
+        for _ in range(squeeze_dims):
+            x_hat = x_hat.squeeze(0)
+        x_hat = x_hat.to(y_in.device)
+        return (x_hat, info) if return_preprocess_info else x_hat
+
+
+def build_flowdec(variant="75m", device=None):
+    """The model `config/flowdec_{75m,25s}.yaml` instantiates (hydra replaced by direct calls)."""
+    from .backbones.ncsnpp import NCSNpp
+    from .data.feature_extractors import AmplitudeCompressedComplexSTFT
+    from .data.sigma_models import from_file
+    backbone = NCSNpp(image_size=768, nonlinearity="swish", nf=64, ch_mult=[4, 4, 4, 2], num_res_blocks=1,
+                      attn_resolutions=[], bottleneck_attn=False, resamp_with_conv=True, conditional=True,
+                      fir=True, fir_kernel=[1, 3, 3, 1], skip_rescale=True, resblock_type="biggan",
+                      progressive="output_skip", progressive_input="input_skip", progressive_combine="sum",
+                      init_scale=0.0, embedding_type="fourier", fourier_scale=16, dropout=0.0, num_channels=4,
+                      output_layer_kwargs=dict(kernel_size=1, bias=False, padding="same", padding_mode="zeros"))
+    fe = AmplitudeCompressedComplexSTFT(window_fn="hann", n_fft=1534, sampling_rate=48000, alpha=0.3, beta=0.33,
+                                        n_hops=4)
+    sigma_y = from_file(f"flowdec_autoparams_{variant}.npy", factor=1, kernel_bandwidth=3)
+    m = FlowModel(None, 0.0, sigma_y, backbone=backbone, feature_extractor=fe, sampling_rate=48000, lr=1e-4)
+    m.eval()
+    return m.to(device) if device is not None else m

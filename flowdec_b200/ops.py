@@ -48,3 +48,144 @@ def conv_igemm(srcs, wpacked, bias, out, max_ctas=0):
                            int(out_f32), out.shape[3], npad, B, H, W, max_ctas, _lib.stream_ptr())
     _lib.check(rc, "fd_conv2d_igemm")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# HBM-bound side kernels (csrc/fd_elementwise.cu)
+# ---------------------------------------------------------------------------------------------
+def chan_stats(x, slabs, out=None):
+    """x: bf16 NHWC [B,H,W,C] -> fp32 partial sums [B,S,C,2] (sum, sum of squares per slab)."""
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty(B, slabs, C, 2, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().fd_chan_stats(_lib.ptr(x), B, H * W, C, _lib.ptr(out), slabs, _lib.stream_ptr()),
+               "fd_chan_stats")
+    return out
+
+
+def gn_finalize(parts, chans, count, gamma, beta, groups, eps, out):
+    """parts: 1 or 2 partial-sum tensors [B,S,Ci,2] forming the virtual concat. out: fp32 [B,C,2]."""
+    p1 = parts[0]
+    p2 = parts[1] if len(parts) > 1 else None
+    c2 = chans[1] if len(parts) > 1 else 0
+    B, S = p1.shape[0], p1.shape[1]
+    rc = _lib.lib().fd_gn_finalize(_lib.ptr(p1), chans[0], _lib.ptr(p2), c2, S, B, ctypes.c_double(count),
+                                   _lib.ptr(gamma), _lib.ptr(beta), groups, ctypes.c_float(eps),
+                                   _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "fd_gn_finalize")
+    return out
+
+
+def gn_act_resample(srcs, scale_shift, out, mode, act):
+    """srcs: 1 or 2 bf16 NHWC tensors (virtual concat). mode 0/1/2 = same/down/up."""
+    s1 = srcs[0]
+    s2 = srcs[1] if len(srcs) > 1 else None
+    B, H, W, C1 = s1.shape
+    C2 = s2.shape[3] if s2 is not None else 0
+    rc = _lib.lib().fd_gn_act_resample(_lib.ptr(s1), C1, _lib.ptr(s2), C2, _lib.ptr(scale_shift),
+                                       _lib.ptr(out), B, H, W, mode, int(act), _lib.stream_ptr())
+    _lib.check(rc, "fd_gn_act_resample")
+    return out
+
+
+def pack4(x, y, out):
+    n = x.numel() // 2
+    _lib.check(_lib.lib().fd_pack4(_lib.ptr(x), _lib.ptr(y), _lib.ptr(out), ctypes.c_size_t(n),
+                                   _lib.stream_ptr()), "fd_pack4")
+    return out
+
+
+def fir_down4(x, out):
+    B, H, W, _ = x.shape
+    _lib.check(_lib.lib().fd_fir_down4(_lib.ptr(x), _lib.ptr(out), B, H, W, _lib.stream_ptr()), "fd_fir_down4")
+    return out
+
+
+def pyramid_up_add(lo, add, out):
+    B, H, W, _ = lo.shape
+    _lib.check(_lib.lib().fd_pyramid_up_add(_lib.ptr(lo), _lib.ptr(add), _lib.ptr(out), B, H, W,
+                                            _lib.stream_ptr()), "fd_pyramid_up_add")
+    return out
+
+
+def conv_in(x4, w, b, out):
+    B, H, W, _ = x4.shape
+    _lib.check(_lib.lib().fd_conv_in(_lib.ptr(x4), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), B, H, W,
+                                     _lib.stream_ptr()), "fd_conv_in")
+    return out
+
+
+def combine(pyr4, w, b, h, out):
+    B, H, W, C = h.shape
+    _lib.check(_lib.lib().fd_combine(_lib.ptr(pyr4), _lib.ptr(w), _lib.ptr(b), _lib.ptr(h), _lib.ptr(out),
+                                     ctypes.c_size_t(B * H * W), C, _lib.stream_ptr()), "fd_combine")
+    return out
+
+
+def output_axpy(pyr4, w_out8, base1, c1, base2, c2, coef, out, v_out=None):
+    """w_out8: host ctypes float[8] (2x4 output-layer weights)."""
+    npix = pyr4.numel() // 4
+    rc = _lib.lib().fd_output_axpy(_lib.ptr(pyr4), w_out8, _lib.ptr(base1), ctypes.c_float(c1),
+                                   _lib.ptr(base2), ctypes.c_float(c2), ctypes.c_float(coef),
+                                   _lib.ptr(out), _lib.ptr(v_out), ctypes.c_size_t(npix), _lib.stream_ptr())
+    _lib.check(rc, "fd_output_axpy")
+    return out
+
+
+def x0_noise(Y, sigma_f64, eps, fac, out):
+    """Y, eps, out: fp32 [B,F,T,2] (= complex64 [B,F,T]); sigma_f64: f64 [F]."""
+    B, Fq, T = Y.shape[0], Y.shape[1], Y.shape[2]
+    rc = _lib.lib().fd_x0(_lib.ptr(Y), _lib.ptr(sigma_f64), _lib.ptr(eps), ctypes.c_float(fac), _lib.ptr(out),
+                          B, Fq, T, _lib.stream_ptr())
+    _lib.check(rc, "fd_x0")
+    return out
+
+
+def fourier_embed(t, Wf, out):
+    _lib.check(_lib.lib().fd_fourier_embed(ctypes.c_float(t), _lib.ptr(Wf), Wf.numel(), _lib.ptr(out),
+                                           _lib.stream_ptr()), "fd_fourier_embed")
+    return out
+
+
+def matvec(inp, Wm, b, out, silu_in=False, add=None, out_scale=1.0):
+    M, K = Wm.shape
+    rc = _lib.lib().fd_matvec(_lib.ptr(inp), K, int(silu_in), _lib.ptr(Wm), _lib.ptr(b), _lib.ptr(add),
+                              ctypes.c_float(out_scale), _lib.ptr(out), M, _lib.stream_ptr())
+    _lib.check(rc, "fd_matvec")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# STFT side (csrc/fd_stft.cu)
+# ---------------------------------------------------------------------------------------------
+def twiddles1534(device):
+    tw = torch.empty(1534, 2, device=device, dtype=torch.float32)
+    _lib.check(_lib.lib().fd_twiddles1534(_lib.ptr(tw), _lib.stream_ptr()), "fd_twiddles1534")
+    return tw
+
+
+def normfac(y2d, mode, out):
+    B, L = y2d.shape
+    _lib.check(_lib.lib().fd_normfac(_lib.ptr(y2d), B, L, int(mode), _lib.ptr(out), _lib.stream_ptr()),
+               "fd_normfac")
+    return out
+
+
+def stft_compress(y2d, nf, window, tw, alpha, beta, out):
+    """y2d fp32 [B,L]; out float2 [B,768,Tp] (as fp32 [B,768,Tp,2])."""
+    B, L = y2d.shape
+    Tp = out.shape[2]
+    rc = _lib.lib().fd_stft1534_compress(_lib.ptr(y2d), B, L, _lib.ptr(nf), _lib.ptr(window), _lib.ptr(tw),
+                                         ctypes.c_float(alpha), ctypes.c_float(beta), Tp, _lib.ptr(out),
+                                         _lib.stream_ptr())
+    _lib.check(rc, "fd_stft1534_compress")
+    return out
+
+
+def istft_decompress(X, L, window, tw, nf, alpha, beta, out):
+    B, Tp = X.shape[0], X.shape[2]
+    rc = _lib.lib().fd_istft1534_decompress(_lib.ptr(X), B, Tp, L, _lib.ptr(window), _lib.ptr(tw), _lib.ptr(nf),
+                                            ctypes.c_float(alpha), ctypes.c_float(beta), _lib.ptr(out),
+                                            _lib.stream_ptr())
+    _lib.check(rc, "fd_istft1534_decompress")
+    return out

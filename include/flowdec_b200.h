@@ -1,0 +1,115 @@
+/* flowdec_b200 — C ABI of libflowdec_b200.so (sm_100a kernels for the FlowDec postfilter path).
+ *
+ * Conventions
+ *   - every function returns 0 on success; non-zero = failure, message via fd_last_error()
+ *     (thread-local).  Kernel launch errors are checked (the reference's pybind op does not,
+ *     op/upfirdn2d_kernel.cu:220-380).
+ *   - all pointers are raw DEVICE pointers owned by the caller unless marked "host"; nothing
+ *     is allocated, freed or synchronised inside; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), re-entrant per stream, CUDA-graph capturable.
+ *   - layouts: activations bf16 NHWC [B,H,W,C] (H = frequency bins, W = STFT frames);
+ *     4-channel pyramids fp32 [B,H,W,4]; spectrograms / ODE state float2 [B,F,T]
+ *     (bit-identical to torch.complex64 [B,1,F,T]); waveforms fp32 [B,L].
+ *
+ * The reference's native boundary for this path is a pybind11 module built at import
+ * (flowdec/backbones/ncsnpp_utils/op/upfirdn2d.cpp:38-48, fused_bias_act.cpp:37-46); the rest
+ * of its hot path is ATen/cuDNN/cuFFT calls from Python.  Each entry below names the reference
+ * code it replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ */
+#ifndef FLOWDEC_B200_H
+#define FLOWDEC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fd_stream_t; /* cudaStream_t */
+
+const char* fd_last_error(void);
+int fd_abi_version(void);
+
+/* ---- NCSN++ convolutions: tcgen05 implicit GEMM ---------------------------------------------
+ * replaces nn.Conv2d -> cuDNN (flowdec/backbones/ncsnpp_utils/layers.py:110-134 as used by
+ * layerspp.py:235,243,245 and ncsnpp.py:218,230) including the res-block's skip path and
+ * (x + h)/sqrt(2) (layerspp.py:278-284), which are folded into extra K segments. */
+struct fd_conv_src {
+  const void* ptr; /* bf16 NHWC [B,H,W,C] */
+  int C;           /* channel pitch of the tensor */
+  int c_begin;     /* first channel consumed (multiple of 8) */
+  int c_count;     /* channels consumed (multiple of 64) */
+  int taps;        /* 9 = 3x3 zero-padded, 1 = 1x1 */
+};
+/* out[b,h,w,o] = bias[o] + sum_seg sum_tap sum_c src_seg[b,h+dh,w+dw,c] * wpacked[o, k(seg,tap,c)]
+ * wpacked: bf16 [npad, ktot], K-major, k ordered segment-major, then tap (kh-major), then channel.
+ * out_is_f32 = 0: out bf16 NHWC [B,H,W,cout], cout == npad in {128,256}
+ * out_is_f32 = 1: out fp32 NHWC [B,H,W,cout], cout <= 16, npad == 16 (the 4-channel pyramid convs)
+ * bias: fp32 [npad] or NULL.  Requires W % 8 == 0 and H % (128 / min(128, pow2 divisor of W)) == 0.
+ * max_ctas: 0 = one persistent CTA per SM. */
+int fd_conv2d_igemm(const struct fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot,
+                    const float* bias, void* out, int out_is_f32, int cout, int npad, int B, int H,
+                    int W, int max_ctas, fd_stream_t stream);
+
+/* ---- GroupNorm + SiLU + FIR resampling ------------------------------------------------------
+ * replace nn.GroupNorm / nn.SiLU (layerspp.py:229,241,253,274; ncsnpp.py:216,228) and
+ * upsample_2d / downsample_2d -> upfirdn2d (up_or_down_sampling.py:220-282,
+ * op/upfirdn2d.cpp:38-48, op/upfirdn2d_kernel.cu:118-218). */
+/* partial[b][s][c][0..1] = sum / sum of squares of x over slab s of the HW pixels (S slabs) */
+int fd_chan_stats(const void* x_bf16, int B, int HW, int C, float* partial, int S, fd_stream_t stream);
+/* group statistics over the virtual channel concat [part1 (C1), part2 (C2)] (fp64 reduction) ->
+ * scale_shift fp32 [B, C1+C2, 2]:  y = x * scale + shift == GroupNorm(x) with gamma/beta */
+int fd_gn_finalize(const float* part1, int C1, const float* part2, int C2, int S, int B, double count,
+                   const float* gamma, const float* beta, int groups, float eps, float* scale_shift,
+                   fd_stream_t stream);
+/* out = FIR_mode( apply_act ? SiLU(x*scale+shift) : x ) over the virtual concat [src1, src2];
+ * mode 0 none, 1 down x2 ([1,3,3,1]/8 per axis, pad (1,1)), 2 up x2 ([1,3,3,1]/4, pad (2,1));
+ * out bf16 NHWC [B,H',W',C1+C2] */
+int fd_gn_act_resample(const void* src1, int C1, const void* src2, int C2, const float* scale_shift,
+                       void* out, int B, int H, int W, int mode, int apply_act, fd_stream_t stream);
+
+/* ---- 4-channel paths of NCSN++ ---------------------------------------------------------------*/
+/* ncsnpp.py:261,401-404: (re x, im x, re y, im y) -> fp32 [npix,4] */
+int fd_pack4(const void* x_f2, const void* y_f2, void* out4, size_t npix, fd_stream_t stream);
+/* ncsnpp.py:300 pyramid_downsample on the 4-channel input pyramid */
+int fd_fir_down4(const void* in4, void* out4, int B, int H, int W, fd_stream_t stream);
+/* ncsnpp.py:355,360: out = FIR_up(lo[B,H,W,4]) + add[B,2H,2W,4] (out may alias add) */
+int fd_pyramid_up_add(const void* lo4, const void* add4, void* out4, int B, int H, int W, fd_stream_t stream);
+/* ncsnpp.py:284 input conv 3x3 4->64 (w fp32 OIHW [64,4,3,3]) -> bf16 NHWC [B,H,W,64] */
+int fd_conv_in(const void* in4, const float* w, const float* bias, void* out, int B, int H, int W,
+               fd_stream_t stream);
+/* layerspp.py:62-69 Combine('sum'): out = h + Conv1x1_{4->C}(pyr) + bias   (w fp32 [C,4]) */
+int fd_combine(const void* pyr4, const float* w, const float* bias, const void* h, void* out,
+               size_t npix, int C, fd_stream_t stream);
+/* ncsnpp.py:398 output 1x1 conv (w_out_host8 = HOST pointer to the 2x4 weights) fused with one
+ * explicit ODE stage (torchdyn Euler/Midpoint step, flowdec/sampling/solvers.py:15-57):
+ *   v = W_out * pyr ; out = c1*base1 + c2*base2 + coef*v   (NULL bases / out / v_out allowed) */
+int fd_output_axpy(const void* pyr4, const float* w_out_host8, const void* base1, float c1,
+                   const void* base2, float c2, float coef, void* out, void* v_out, size_t npix,
+                   fd_stream_t stream);
+/* model.py:512,530-536: out = Y + fac * (float)(sigma[f] (f64) * eps) */
+int fd_x0(const void* Y, const double* sigma, const void* eps, float fac, void* out, int B, int F, int T,
+          fd_stream_t stream);
+
+/* ---- time embedding (ncsnpp.py:263-274, layerspp.py:49-51,270-272) --------------------------*/
+int fd_fourier_embed(float t, const float* Wf, int nf, float* out /* [2*nf] */, fd_stream_t stream);
+/* out[m] = (add ? add[m] : 0) + out_scale * (b[m] + sum_k W[m,k] * (silu_in ? SiLU(in[k]) : in[k])) */
+int fd_matvec(const float* in, int K, int silu_in, const float* W, const float* b, const float* add,
+              float out_scale, float* out, int M, fd_stream_t stream);
+
+/* ---- waveform <-> compressed spectrogram (util/other.py:25-82, feature_extractors.py:86-139) -*/
+int fd_twiddles1534(void* tw /* float2 [1534] */, fd_stream_t stream);
+/* mode 1: normfac[b] = max|y[b,:]| with values <= 1e-8 replaced by 1 ; mode 0: 1 */
+int fd_normfac(const float* y, int B, int L, int mode, float* normfac, fd_stream_t stream);
+/* out float2 [B,768,Tp]: beta*|X|^alpha e^{j angle X} of the n_fft=1534/hop=384 centred STFT of
+ * y/normfac; frames >= 1+L/384 are zero (pad_spec 'zero') */
+int fd_stft1534_compress(const float* y, int B, int L, const float* normfac, const float* window,
+                         const void* tw, float alpha, float beta, int Tp, void* out, fd_stream_t stream);
+/* inverse: decompress, overlap-add iSTFT (torch.istft semantics incl. length=L), times normfac */
+int fd_istft1534_decompress(const void* X, int B, int Tp, int L, const float* window, const void* tw,
+                            const float* normfac, float alpha, float beta, float* out, fd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWDEC_B200_H */

@@ -1,0 +1,79 @@
+"""CPU tests (no GPU): the oracle against the golden vectors produced by the unmodified
+reference, and — where /root/reference is present — against the reference itself."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from flowdec_b200.util.synth import synth_state_dict
+from oracle import flowdec_oracle as O
+from oracle import ref_shim
+from oracle.make_golden import golden_inputs
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "flowdec_75m_seed0.npz")
+
+
+@pytest.fixture(scope="module")
+def sd():
+    from flowdec_b200.model import build_flowdec
+    m = build_flowdec("75m")
+    return synth_state_dict(m.state_dict(), seed=0)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return {k: torch.from_numpy(v) for k, v in np.load(GOLD).items()}
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_feature_path_vs_golden(sd, gold):
+    I = golden_inputs()
+    w = sd["feature_extractor.complex_stft.window"]
+    Y, info = O.preprocess(I["y"], w)
+    assert rel_l2(torch.view_as_real(Y), gold["preprocess_Y"]) < 1e-6
+    assert torch.equal(info["normfac"], gold["normfac"])
+    assert rel_l2(O.postprocess(Y, info, w), gold["postprocess_of_Y"]) < 1e-6
+
+
+def test_fir_vs_golden(gold):
+    xf = torch.randn(2, 8, 12, 16, generator=torch.Generator().manual_seed(5))
+    assert rel_l2(O.fir_down2(xf), gold["fir_down"]) < 1e-6
+    assert rel_l2(O.fir_up2(xf), gold["fir_up"]) < 1e-6
+
+
+def test_backbone_vs_golden(sd, gold):
+    I = golden_inputs()
+    with torch.no_grad():
+        v = O.ncsnpp_forward(sd, I["X"], I["Y"], I["t"])
+    assert rel_l2(torch.view_as_real(v), gold["backbone_v"]) < 1e-5
+
+
+@pytest.mark.parametrize("N,solver", [(1, "euler"), (1, "midpoint")])
+def test_enhance_vs_golden(sd, gold, N, solver):
+    I = golden_inputs()
+    with torch.no_grad():
+        x = O.enhance(sd, I["y"], N=N, solver=solver, eps=I["eps"])
+    assert rel_l2(x, gold[f"enhance_{solver}_N{N}"]) < 1e-4
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present on this machine")
+def test_oracle_vs_live_reference_small():
+    """cheap live pin: a 2-level, nf=16 backbone of the same family, reference vs oracle"""
+    R = ref_shim.load_reference()
+    kw = dict(ref_shim.BACKBONE_KW)
+    kw.update(image_size=64, nf=16, ch_mult=[2, 2])
+    net = R.ncsnpp.NCSNpp(**kw)
+    sd = synth_state_dict({"backbone." + k: v for k, v in net.state_dict().items()}, seed=3)
+    net.load_state_dict({k[len("backbone."):]: v for k, v in sd.items()})
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 1, 64, 16, dtype=torch.complex64, generator=g)
+    y = torch.randn(2, 1, 64, 16, dtype=torch.complex64, generator=g)
+    t = torch.tensor([0.7])
+    with torch.no_grad():
+        ref = net(x, y, t)
+        mine = O.ncsnpp_forward(sd, x, y, t, num_resolutions=2)
+    assert rel_l2(torch.view_as_real(mine), torch.view_as_real(ref)) < 1e-5
