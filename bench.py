@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — FlowDec postfilter throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference algorithm on host CPU
+
+Metric: 48 kHz audio-seconds generated per wall-second for `flowdec_75m` at NFE = 6
+(midpoint, N = 3).  One "step" = one `FlowModel.enhance` pass over one batch of synthetic
+clips: per GPU 32 clips x 2 s (BASELINE.json configs[1]); N GPUs = N independent shards, no
+data-path collective (weak scaling).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 48000
+MACS_PER_FRAME = 5_861_842_944  # conv MACs per padded STFT frame column
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
+    ap.add_argument("--seconds", type=float, default=2.0, help="clip length")
+    ap.add_argument("--N", type=int, default=3)
+    ap.add_argument("--solver", default="midpoint")
+    ap.add_argument("--variant", default="75m")
+    ap.add_argument("--max-batch", type=int, default=0, help="clips per backbone pass (0 = model default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def nfe_of(N, solver):
+    return N * (1 if solver == "euler" else 2)
+
+
+def padded_frames(L):
+    T = 1 + L // 384
+    return T + (64 - T % 64) % 64
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), "measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_time(threads, seconds_clip=0.5, N=1, solver="midpoint"):
+    """Times the CPU oracle (port of the reference algorithm) on a bounded sample: one clip of
+    `seconds_clip` at NFE = 2 (midpoint N=1).  Cost is linear in B*Tp*NFE (conv dominated,
+    BASELINE.md §4), so audio-s/s at NFE 6 = clip_seconds / (t * 6/NFE_sample)."""
+    from flowdec_b200.model import build_flowdec
+    from flowdec_b200.util.synth import synth_state_dict, synth_waveforms
+    from oracle import flowdec_oracle as O
+    torch.set_num_threads(threads)
+    sd = synth_state_dict(build_flowdec("75m").state_dict(), seed=0)
+    L = int(seconds_clip * SR)
+    y = synth_waveforms(1, L, seed=1234)
+    g = torch.Generator().manual_seed(4321)
+    eps = torch.randn(1, 1, 768, padded_frames(L), dtype=torch.complex64, generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.enhance(sd, y, N=N, solver=solver, eps=eps)
+    dt = time.perf_counter() - t0
+    nfe = nfe_of(N, solver)
+    # scale padded frames of the sample (64 for 0.5 s) to the frames/second of the 2 s workload (128/s)
+    frames_sample = padded_frames(L)
+    sec_per_frame_nfe = dt / (frames_sample * nfe)
+    return dt, sec_per_frame_nfe, f"oracle port, 1 clip x {seconds_clip} s ({frames_sample} frames), {solver} N={N} (NFE {nfe}), {dt:.1f} s CPU; scaled linearly in frames x NFE"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    L = int(args.seconds * SR)
+    Tp = padded_frames(L)
+    nfe = nfe_of(args.N, args.solver)
+    times = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        dt, spf, sample = cpu_port_time(threads)
+        if i >= args.warmup:
+            times.append(spf)
+        if i == 0 and dt > 60:      # keep the whole run within minutes
+            times = [spf]
+            break
+    spf = sum(times) / len(times)
+    # one step of the workload = batch clips of `seconds`, NFE evaluations of Tp frames each
+    t_step = spf * Tp * nfe * args.batch * args.gpus
+    value = args.batch * args.gpus * args.seconds / t_step
+    line = {
+        "impl": "reference", "metric": "48kHz audio-seconds/sec (RTF^-1) flowdec_75m NFE=6", "value": value,
+        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    L = int(args.seconds * SR)
+    return {"workload": f"flowdec_{args.variant} postfilter enhance(): {args.batch} clips x {args.seconds:g} s @48kHz per GPU, "
+                        f"{args.solver} N={args.N} (NFE {nfe_of(args.N, args.solver)}), Tp={padded_frames(L)} frames",
+            "per_gpu_batch": args.batch, "clip_seconds": args.seconds, "nfe": nfe_of(args.N, args.solver),
+            "solver": args.solver, "sharding": f"dp{args.gpus} (clip batch, no data-path collective)",
+            "l2": "working set (multi-GB activations per micro-batch) >> 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from flowdec_b200 import _lib, ops
+    from flowdec_b200.model import build_flowdec
+    from flowdec_b200.util.synth import synth_state_dict, synth_waveforms
+
+    model = build_flowdec(args.variant)
+    model.load_state_dict(synth_state_dict(model.state_dict(), seed=0))
+    model = model.to(dev)
+    if args.max_batch:
+        model.max_batch = args.max_batch
+    L = int(args.seconds * SR)
+    B = args.batch
+    nfe = nfe_of(args.N, args.solver)
+    Tp = padded_frames(L)
+    # clips are indexed globally so that every shard is the same regardless of world size
+    y_host = synth_waveforms(B, L, seed=1234 + rank * B).pin_memory()
+    y_dev = y_host.to(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (first call eager + packs weights, second captures the CUDA graph) ----
+    for _ in range(max(args.warmup, 3)):
+        out = model.enhance(y_dev, N=args.N, solver=args.solver)
+    torch.cuda.synchronize()
+
+    # ---- kernel launches per step (eager count) ----
+    model.use_cuda_graph = False
+    n0 = _lib.LAUNCHES
+    model.enhance(y_dev, N=args.N, solver=args.solver)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.LAUNCHES - n0
+    model.use_cuda_graph = True
+
+    # ---- timed region: device-resident inputs ----
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ncu_range = bool(os.environ.get("FD_NCU_RANGE"))   # `ncu --profile-from-start off` captures only this region
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
+    e0.record()
+    for _ in range(args.steps):
+        out = model.enhance(y_dev, N=args.N, solver=args.solver)
+    e1.record()
+    if ncu_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+
+    # ---- end to end: pinned host input -> H2D -> enhance -> D2H ----
+    for _ in range(1):
+        model.enhance(y_host, N=args.N, solver=args.solver)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        out_host = model.enhance(y_host, N=args.N, solver=args.solver)   # returns on y's device (CPU): D2H inside
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    assert out_host.device.type == "cpu" and torch.isfinite(out_host).all()
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    audio_s = B * world * args.seconds * args.steps
+    value = audio_s / (ms * 1e-3)
+    value_e2e = audio_s / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (tcgen05 conv), one instrumented eager step on rank 0 ----
+    roofline = None
+    if rank == 0:
+        model.use_cuda_graph = False
+        ops.PROFILE = []
+        torch.cuda.synchronize()
+        model.enhance(y_dev, N=args.N, solver=args.solver)
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        model.use_cuda_graph = True
+        conv_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+        conv_flops = sum(f for _, _, f in prof)
+        peak, how = load_peaks()
+        algo_flops_step = 2.0 * MACS_PER_FRAME * B * Tp * nfe
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": how, "launches": len(prof), "kernel_ms_per_step": conv_ms,
+                    "kernel_share_of_step": conv_ms / (ms / args.steps),
+                    "algorithmic_tflop_per_step": algo_flops_step / 1e12,
+                    "whole_step_tflops": algo_flops_step / (ms / args.steps * 1e-3) / 1e12,
+                    "whole_step_frac": algo_flops_step / (ms / args.steps * 1e-3) / 1e12 / peak}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        dt, spf, sample = cpu_port_time(threads)
+        v = args.seconds / (spf * Tp * nfe)
+        cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "48kHz audio-seconds/sec (RTF^-1) flowdec_75m NFE=6", "value": value, "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 (tensor-core operands, fp32 accumulate; STFT/ODE/GroupNorm statistics fp32)",
+            "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": value_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * L * 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,7 +73,12 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0   # number of successful fd_* kernel-launching calls (bench.py's gpu_launches)
+
+
 def check(rc, what):
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         msg = lib().fd_last_error().decode("utf-8", "replace")
         raise FlowDecNativeError(f"{what} failed (status {rc}): {msg}")

@@ -350,8 +350,9 @@ class NCSNpp(nn.Module):
             skip = list(srcs)
         wp = self._skip_weight(e, [s.shape[3] for s in skip], cout)
         out = self._ws.get(f"rb{i}", (B, Ho, Wo, cout), torch.bfloat16, dev)
+        algo_k = 9 * cout + (cin if hasattr(m, "Conv_2") else 0)
         ops.conv_igemm([(a1, 0, cout, 9)] + [(s, 0, s.shape[3], 1) for s in skip], wp, e["b1"], out,
-                       self.max_ctas)
+                       self.max_ctas, algo_k=algo_k)
         scache.pop(out.data_ptr(), None)
         return out
 

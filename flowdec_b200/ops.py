@@ -9,6 +9,10 @@ import torch
 
 from . import _lib
 
+# when set to a list, conv_igemm appends (start_event, end_event, algorithmic_flops) per launch
+# (bench.py's roofline leg; events are recorded on the launching stream)
+PROFILE = None
+
 
 def pack_conv_weight(segments, npad):
     """Pack conv weights for fd_conv2d_igemm.
@@ -29,7 +33,7 @@ def pack_conv_weight(segments, npad):
     return wp.contiguous()
 
 
-def conv_igemm(srcs, wpacked, bias, out, max_ctas=0):
+def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None):
     """srcs: list of (tensor NHWC bf16, c_begin, c_count, taps). out: NHWC bf16 [.., npad] or fp32 [.., cout<=16]."""
     L = _lib.lib()
     n = len(srcs)
@@ -44,9 +48,20 @@ def conv_igemm(srcs, wpacked, bias, out, max_ctas=0):
         arr[i].taps = taps
     npad, ktot = wpacked.shape
     out_f32 = out.dtype == torch.float32
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = L.fd_conv2d_igemm(arr, n, _lib.ptr(wpacked), ktot, _lib.ptr(bias), _lib.ptr(out),
                            int(out_f32), out.shape[3], npad, B, H, W, max_ctas, _lib.stream_ptr())
     _lib.check(rc, "fd_conv2d_igemm")
+    if PROFILE is not None:
+        e1.record()
+        # algorithmic FLOPs: real output channels, and K without the identity-skip segment that
+        # stands in for the res-block's "+ x" (an implementation device, not reference arithmetic)
+        k_algo = sum(cc * taps for (_, _, cc, taps) in srcs)
+        if algo_k is not None:
+            k_algo = algo_k
+        PROFILE.append((e0, e1, 2.0 * B * H * W * out.shape[3] * k_algo))
     return out
 
 
