@@ -179,6 +179,7 @@ class NCSNpp(nn.Module):
         self._temb_cache = {}
         self._ws = _Workspace()
         self.stats_slabs = 64
+        self.fuse_stats = True     # GroupNorm partial sums produced by the conv epilogue
         self.max_ctas = 0
 
     # ------------------------------------------------------------------ parameter management
@@ -314,8 +315,8 @@ class NCSNpp(nn.Module):
             cache[k] = p
         return p
 
-    def _gn_act(self, srcs, gamma, beta, mode, scache, name):
-        """a = FIR?(SiLU(GroupNorm(cat(srcs)))) as one bf16 NHWC tensor."""
+    def _gn_act(self, srcs, gamma, beta, mode, scache, name, raw_name=None):
+        """a = FIR?(SiLU(GroupNorm(cat(srcs)))) as one bf16 NHWC tensor (+ FIR(cat(srcs)) if raw_name)."""
         B, H, W = srcs[0].shape[:3]
         C = sum(s.shape[3] for s in srcs)
         parts = [self._partials(s, scache) for s in srcs]
@@ -323,10 +324,11 @@ class NCSNpp(nn.Module):
         ops.gn_finalize(parts, [s.shape[3] for s in srcs], H * W, gamma, beta, min(C // 4, 32), 1e-6, ss)
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
         a = self._ws.get(name, (B, Ho, Wo, C), torch.bfloat16, srcs[0].device)
-        ops.gn_act_resample(srcs, ss, a, mode, True)
-        return a
+        raw = self._ws.get(raw_name, (B, Ho, Wo, C), torch.bfloat16, srcs[0].device) if raw_name else None
+        ops.gn_act_resample(srcs, ss, a, mode, out_raw=raw)
+        return (a, raw) if raw_name else a
 
-    def _resblock(self, i, srcs, tb, scache):
+    def _resblock(self, i, srcs, tb, scache, want_stats=True):
         """reference layerspp.py:252-284; srcs = virtual concat of bf16 NHWC tensors."""
         m = self.all_modules[i]
         e = self._prepared[i]
@@ -336,24 +338,33 @@ class NCSNpp(nn.Module):
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
         cin, cout = m.in_ch, m.out_ch
         assert sum(s.shape[3] for s in srcs) == cin
-        a0 = self._gn_act(srcs, e["g0"], e["be0"], mode, scache, "act")
+        if mode != 0:
+            a0, xr = self._gn_act(srcs, e["g0"], e["be0"], mode, scache, "act", raw_name="xr")
+        else:
+            a0 = self._gn_act(srcs, e["g0"], e["be0"], mode, scache, "act")
         h1 = self._ws.get("h1", (B, Ho, Wo, cout), torch.bfloat16, dev)
-        ops.conv_igemm([(a0, 0, cin, 9)], e["w0"], tb[i], h1, self.max_ctas)
         scache.pop(h1.data_ptr(), None)
+        st_h1 = None
+        if self.fuse_stats:
+            st_h1 = self._ws.get("h1_stats", (B, ops.conv_stats_slabs(Ho, Wo), cout, 2), torch.float32, dev)
+            scache[h1.data_ptr()] = st_h1
+        ops.conv_igemm([(a0, 0, cin, 9)], e["w0"], tb[i], h1, self.max_ctas, stats=st_h1)
         a1 = self._gn_act([h1], e["g1"], e["be1"], 0, scache, "act")
         scache.pop(h1.data_ptr(), None)
         if mode != 0:
-            xr = self._ws.get("xr", (B, Ho, Wo, cin), torch.bfloat16, dev)
-            ops.gn_act_resample(srcs, None, xr, mode, False)
             skip = [xr]
         else:
             skip = list(srcs)
         wp = self._skip_weight(e, [s.shape[3] for s in skip], cout)
         out = self._ws.get(f"rb{i}", (B, Ho, Wo, cout), torch.bfloat16, dev)
         algo_k = 9 * cout + (cin if hasattr(m, "Conv_2") else 0)
-        ops.conv_igemm([(a1, 0, cout, 9)] + [(s, 0, s.shape[3], 1) for s in skip], wp, e["b1"], out,
-                       self.max_ctas, algo_k=algo_k)
         scache.pop(out.data_ptr(), None)
+        st_out = None
+        if self.fuse_stats and want_stats:
+            st_out = self._ws.get(f"rb{i}_stats", (B, ops.conv_stats_slabs(Ho, Wo), cout, 2), torch.float32, dev)
+            scache[out.data_ptr()] = st_out
+        ops.conv_igemm([(a1, 0, cout, 9)] + [(s, 0, s.shape[3], 1) for s in skip], wp, e["b1"], out,
+                       self.max_ctas, algo_k=algo_k, stats=st_out)
         return out
 
     # ------------------------------------------------------------------ forward

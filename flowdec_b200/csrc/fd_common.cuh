@@ -37,8 +37,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// SiLU via ex2.approx + rcp.approx (2 MUFU ops, ~2^-21 relative error)
 __device__ __forceinline__ float silu_f(float v) {
-  return v / (1.0f + __expf(-v));
+  return __fdividef(v, 1.0f + __expf(-v));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -48,6 +48,7 @@ struct ConvParams {
   int num_tiles;
   const float* bias;     // [Npad] or nullptr
   float* out_f32;        // fp32 NHWC [B,H,W,cout_valid] (OUT_F32 kernels only)
+  float* stats;          // optional GroupNorm partials [B, 4*tiles_per_img, N, 2] (bf16-output kernels)
   int cout_valid;
 };
 
@@ -60,6 +61,51 @@ struct ConvCfg {
   static constexpr int kSmemBytes =
       1024 + kStages * (kABytes + kBBytes) + kOutBytes + N * 4 + 256;
 };
+
+// One 32-column half of an epilogue chunk for this lane's pixel row: + bias, bf16 pack into the
+// 128B-swizzled staging tile (16-byte chunks j0..j0+3 of the row), and optionally the
+// GroupNorm partial sums of the 32 columns over the warp's 32 rows.  The column reduction is a
+// transpose-reduce butterfly (31 shuffles per statistic instead of 32*5): after the xor-16 step
+// every lane keeps 16 columns, ... after xor-1 lane L holds the total of column L.
+__device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], const float* bs, uint8_t* rowp,
+                                              int row, int j0, float* stat_dst, int lane) {
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + bs[i];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 q;
+    q.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+    q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+    q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+    q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+    *reinterpret_cast<uint4*>(rowp + (((j0 + j) ^ (row & 7)) << 4)) = q;
+  }
+  if (stat_dst != nullptr) {
+    float q[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) q[i] = f[i] * f[i];
+#define FD_BFLY(OFF, HALF)                                                      \
+    {                                                                           \
+      const bool up = (lane & OFF) != 0;                                        \
+      _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                        \
+        const float ks = up ? f[HALF + i] : f[i];                               \
+        const float ss = up ? f[i] : f[HALF + i];                               \
+        const float kq = up ? q[HALF + i] : q[i];                               \
+        const float sq = up ? q[i] : q[HALF + i];                               \
+        f[i] = ks + __shfl_xor_sync(0xffffffffu, ss, OFF);                      \
+        q[i] = kq + __shfl_xor_sync(0xffffffffu, sq, OFF);                      \
+      }                                                                         \
+    }
+    FD_BFLY(16, 16)
+    FD_BFLY(8, 8)
+    FD_BFLY(4, 4)
+    FD_BFLY(2, 2)
+    FD_BFLY(1, 1)
+#undef FD_BFLY
+    *reinterpret_cast<float2*>(stat_dst + lane * 2) = make_float2(f[0], q[0]);
+  }
+}
 
 template <int N, bool OUT_F32>
 __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
@@ -217,6 +263,9 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         }
       } else {
         constexpr int kChunks = N / 64;
+        const int slab = rem * 4 + ew;   // GroupNorm partial-sum slab of this warp's 32 pixels
+        float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * (tiles_per_img * 4) + slab) * N) * 2
+                                  : nullptr;
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ++ch) {
           uint32_t v0[32], v1[32];
@@ -233,32 +282,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           named_bar_sync(1, 128);
           const float* bs = sBias + ch * 64;
           uint8_t* rowp = stg + row * 128;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 q;
-            q.x = pack_bf16x2(__uint_as_float(v0[8 * j + 0]) + bs[8 * j + 0],
-                              __uint_as_float(v0[8 * j + 1]) + bs[8 * j + 1]);
-            q.y = pack_bf16x2(__uint_as_float(v0[8 * j + 2]) + bs[8 * j + 2],
-                              __uint_as_float(v0[8 * j + 3]) + bs[8 * j + 3]);
-            q.z = pack_bf16x2(__uint_as_float(v0[8 * j + 4]) + bs[8 * j + 4],
-                              __uint_as_float(v0[8 * j + 5]) + bs[8 * j + 5]);
-            q.w = pack_bf16x2(__uint_as_float(v0[8 * j + 6]) + bs[8 * j + 6],
-                              __uint_as_float(v0[8 * j + 7]) + bs[8 * j + 7]);
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = q;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 q;
-            q.x = pack_bf16x2(__uint_as_float(v1[8 * j + 0]) + bs[32 + 8 * j + 0],
-                              __uint_as_float(v1[8 * j + 1]) + bs[32 + 8 * j + 1]);
-            q.y = pack_bf16x2(__uint_as_float(v1[8 * j + 2]) + bs[32 + 8 * j + 2],
-                              __uint_as_float(v1[8 * j + 3]) + bs[32 + 8 * j + 3]);
-            q.z = pack_bf16x2(__uint_as_float(v1[8 * j + 4]) + bs[32 + 8 * j + 4],
-                              __uint_as_float(v1[8 * j + 5]) + bs[32 + 8 * j + 5]);
-            q.w = pack_bf16x2(__uint_as_float(v1[8 * j + 6]) + bs[32 + 8 * j + 6],
-                              __uint_as_float(v1[8 * j + 7]) + bs[32 + 8 * j + 7]);
-            *reinterpret_cast<uint4*>(rowp + (((j + 4) ^ (row & 7)) << 4)) = q;
-          }
+          epilogue_half(v0, bs, rowp, row, 0, stat_row ? stat_row + (ch * 64) * 2 : nullptr, lane);
+          epilogue_half(v1, bs + 32, rowp, row, 4, stat_row ? stat_row + (ch * 64 + 32) * 2 : nullptr, lane);
           fence_proxy_async_smem();
           named_bar_sync(2, 128);
           if (leader) {
@@ -378,7 +403,7 @@ struct fd_conv_src {
 
 extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot,
                                const float* bias, void* out, int out_is_f32, int cout, int npad,
-                               int B, int H, int W, int max_ctas, cudaStream_t stream) {
+                               int B, int H, int W, float* stats, int max_ctas, cudaStream_t stream) {
   using namespace fd;
   FD_REQUIRE(nsrc >= 1 && nsrc <= kMaxSeg, "fd_conv2d_igemm: nsrc=%d out of range [1,%d]", nsrc, kMaxSeg);
   FD_REQUIRE(npad == 16 || npad == 128 || npad == 256, "fd_conv2d_igemm: npad=%d unsupported", npad);
@@ -415,7 +440,9 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
   p.num_tiles = B * p.tiles_h * p.tiles_w;
   p.bias = bias;
   p.cout_valid = cout;
+  p.stats = stats;
   if (out_is_f32) {
+    FD_REQUIRE(stats == nullptr, "fd_conv2d_igemm: stats are produced by the bf16-output kernels only");
     FD_REQUIRE(npad == 16 && cout >= 1 && cout <= 16, "fd_conv2d_igemm: fp32 output needs npad=16");
     p.out_f32 = static_cast<float*>(out);
     return launch_conv<16, true>(p, max_ctas, stream);

@@ -85,9 +85,9 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const __nv_bfloat16* __
 
 // one block per (group, sample): mean / rstd over the group's channels of the virtual concat
 // [src1 (C1 channels), src2 (C2 channels)], then per-channel scale/shift.
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part1, int C1,
-                                                          const float* __restrict__ part2, int C2,
-                                                          int S, double count,
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part1, int C1, int S1,
+                                                          const float* __restrict__ part2, int C2, int S2,
+                                                          double count,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, int groups,
                                                           float eps, float* __restrict__ scale_shift) {
@@ -96,13 +96,19 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
   const int C = C1 + C2;
   const int cpg = C / groups;
   double s = 0.0, q = 0.0;
-  for (int i = threadIdx.x; i < cpg * S; i += 128) {
-    const int c = g * cpg + i / S;
-    const int sl = i % S;
-    const float* p = (c < C1) ? part1 + ((static_cast<size_t>(b) * S + sl) * C1 + c) * 2
-                              : part2 + ((static_cast<size_t>(b) * S + sl) * C2 + (c - C1)) * 2;
-    s += static_cast<double>(p[0]);
-    q += static_cast<double>(p[1]);
+  // channels of the group may straddle the concat seam: walk them one by one, slabs strided
+  for (int ci = 0; ci < cpg; ++ci) {
+    const int c = g * cpg + ci;
+    const bool first = c < C1;
+    const int S = first ? S1 : S2;
+    const int Cs = first ? C1 : C2;
+    const int cc = first ? c : c - C1;
+    const float* base = (first ? part1 : part2) + (static_cast<size_t>(b) * S * Cs + cc) * 2;
+    for (int sl = threadIdx.x; sl < S; sl += 128) {
+      const float2 v = *reinterpret_cast<const float2*>(base + static_cast<size_t>(sl) * Cs * 2);
+      s += static_cast<double>(v.x);
+      q += static_cast<double>(v.y);
+    }
   }
   ssum[threadIdx.x] = s;
   ssq[threadIdx.x] = q;
@@ -129,79 +135,165 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------
-// a = [FIR](SiLU(x * scale + shift)) over the virtual concat [src1, src2] -> bf16 NHWC.
-// MODE 0: same resolution, 1: FIR down x2, 2: FIR up x2.  ACT=false: raw FIR of x (skip path).
-// One thread per (output pixel, 8 channels).
+// act = [FIR](SiLU(x * scale + shift)) and (optionally) raw = [FIR](x) over the virtual concat
+// [src1, src2] -> bf16 NHWC.  MODE 0: same resolution, 1: FIR down x2, 2: FIR up x2.
+// grid.y = one input-resolution row unit, threads over (column unit, channel octet):
+//   MODE 0: unit = 1 pixel;  MODE 1: unit = 2x2 output patch (6x6 inputs, each activated once);
+//   MODE 2: unit = 1 input pixel -> 2x2 output quad (3x3 inputs).
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool ACT>
+struct Oct {
+  const __nv_bfloat16* img;  // source image base (+ channel offset) of this sample
+  int Cs;                    // channel pitch of that source
+  float sc[8], sh[8];
+};
+
+template <bool ACT>
+__device__ __forceinline__ void load_act(const Oct& o, int H, int W, int hi, int wi, float (&a)[8],
+                                         float (&r)[8], bool want_raw) {
+  if (hi < 0 || hi >= H || wi < 0 || wi >= W) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = r[i] = 0.f;
+    return;
+  }
+  float v[8];
+  load8(o.img + (static_cast<size_t>(hi) * W + wi) * o.Cs, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (want_raw) r[i] = v[i];
+    a[i] = ACT ? silu_f(fmaf(v[i], o.sc[i], o.sh[i])) : v[i];
+  }
+}
+
+template <int MODE, bool ACT, bool RAW>
 __global__ void __launch_bounds__(256) gn_act_resample_kernel(
     const __nv_bfloat16* __restrict__ src1, int C1, const __nv_bfloat16* __restrict__ src2, int C2,
-    const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+    const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ out,
+    __nv_bfloat16* __restrict__ out_raw, int H, int W) {
   const int C = C1 + C2;
   const int oct = C >> 3;
-  const int Ho = (MODE == 1) ? H / 2 : (MODE == 2 ? H * 2 : H);
-  const int Wo = (MODE == 1) ? W / 2 : (MODE == 2 ? W * 2 : W);
-  const size_t total = static_cast<size_t>(B) * Ho * Wo * oct;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int o = static_cast<int>(idx % oct);
-    size_t pix = idx / oct;
-    const int wo = static_cast<int>(pix % Wo);
-    pix /= Wo;
-    const int ho = static_cast<int>(pix % Ho);
-    const int b = static_cast<int>(pix / Ho);
-    const int c0 = o * 8;
-    const __nv_bfloat16* src;
-    int Cs, cs;
-    if (c0 < C1) {
-      src = src1; Cs = C1; cs = c0;
-    } else {
-      src = src2; Cs = C2; cs = c0 - C1;
-    }
-    float sc[8], sh[8];
+  // units along W at input resolution (MODE 1: pairs of output columns)
+  const int UW = (MODE == 1) ? W / 4 : W;
+  const int UH = (MODE == 1) ? H / 4 : H;
+  const int row_unit = blockIdx.y % UH;
+  const int b = blockIdx.y / UH;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= UW * oct) return;
+  const int uw = t / oct;
+  const int o8 = t - uw * oct;
+  const int c0 = o8 * 8;
+  Oct o;
+  {
+    const bool first = c0 < C1;
+    o.Cs = first ? C1 : C2;
+    o.img = (first ? src1 : src2) + static_cast<size_t>(b) * H * W * o.Cs + (first ? c0 : c0 - C1);
     if (ACT) {
       const float4* ss = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(b) * C + c0) * 2);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 t = ss[i];
-        sc[2 * i] = t.x; sh[2 * i] = t.y; sc[2 * i + 1] = t.z; sh[2 * i + 1] = t.w;
+        const float4 q = ss[i];
+        o.sc[2 * i] = q.x; o.sh[2 * i] = q.y; o.sc[2 * i + 1] = q.z; o.sh[2 * i + 1] = q.w;
       }
     }
-    const __nv_bfloat16* img = src + static_cast<size_t>(b) * H * W * Cs + cs;
-    float acc[8];
+  }
+  if (MODE == 0) {
+    float a[8], r[8];
+    load_act<ACT>(o, H, W, row_unit, uw, a, r, false);
+    store8(out + ((static_cast<size_t>(b) * H + row_unit) * W + uw) * C + c0, a);
+  } else if (MODE == 1) {
+    // outputs (2*row_unit + {0,1}, 2*uw + {0,1}); inputs rows 4*row_unit-1 .. +4, cols 4*uw-1 .. +4
+    const int Ho = H / 2, Wo = W / 2;
+    float acc[2][2][8], racc[2][2][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-
-    auto tap = [&](int hi, int wi, float wgt) {
-      if (hi < 0 || hi >= H || wi < 0 || wi >= W) return;
-      float v[8];
-      load8(img + (static_cast<size_t>(hi) * W + wi) * Cs, v);
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float a = v[i];
-        if (ACT) a = silu_f(fmaf(a, sc[i], sh[i]));
-        acc[i] = fmaf(wgt, a, acc[i]);
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][j][c] = racc[i][j][c] = 0.f;
+    const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+#pragma unroll
+    for (int ri = 0; ri < 6; ++ri) {
+      const int hi = 4 * row_unit - 1 + ri;
+      float h0[8], h1[8], rh0[8], rh1[8];  // horizontal FIR of this input row for the two output columns
+#pragma unroll
+      for (int c = 0; c < 8; ++c) h0[c] = h1[c] = rh0[c] = rh1[c] = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 6; ++ci) {
+        float a[8], r[8];
+        load_act<ACT>(o, H, W, hi, 4 * uw - 1 + ci, a, r, RAW);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (ci < 4) { h0[c] = fmaf(k[ci], a[c], h0[c]); if (RAW) rh0[c] = fmaf(k[ci], r[c], rh0[c]); }
+          if (ci >= 2) { h1[c] = fmaf(k[ci - 2], a[c], h1[c]); if (RAW) rh1[c] = fmaf(k[ci - 2], r[c], rh1[c]); }
+        }
       }
-    };
-
-    if (MODE == 0) {
-      tap(ho, wo, 1.0f);
-    } else if (MODE == 1) {
-      const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) tap(2 * ho - 1 + a, 2 * wo - 1 + bb, k[a] * k[bb]);
-    } else {
-      const int hi = ho >> 1, wi = wo >> 1;
-      const int hn = (ho & 1) ? hi + 1 : hi - 1;  // the 1/4-weight neighbour
-      const int wn = (wo & 1) ? wi + 1 : wi - 1;
-      tap(hi, wi, 0.5625f);
-      tap(hi, wn, 0.1875f);
-      tap(hn, wi, 0.1875f);
-      tap(hn, wn, 0.0625f);
+      for (int c = 0; c < 8; ++c) {
+        if (ri < 4) {
+          acc[0][0][c] = fmaf(k[ri], h0[c], acc[0][0][c]);
+          acc[0][1][c] = fmaf(k[ri], h1[c], acc[0][1][c]);
+          if (RAW) { racc[0][0][c] = fmaf(k[ri], rh0[c], racc[0][0][c]); racc[0][1][c] = fmaf(k[ri], rh1[c], racc[0][1][c]); }
+        }
+        if (ri >= 2) {
+          acc[1][0][c] = fmaf(k[ri - 2], h0[c], acc[1][0][c]);
+          acc[1][1][c] = fmaf(k[ri - 2], h1[c], acc[1][1][c]);
+          if (RAW) { racc[1][0][c] = fmaf(k[ri - 2], rh0[c], racc[1][0][c]); racc[1][1][c] = fmaf(k[ri - 2], rh1[c], racc[1][1][c]); }
+        }
+      }
     }
-    store8(out + ((static_cast<size_t>(b) * Ho + ho) * Wo + wo) * C + c0, acc);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const size_t off = ((static_cast<size_t>(b) * Ho + 2 * row_unit + i) * Wo + 2 * uw + j) * C + c0;
+        store8(out + off, acc[i][j]);
+        if (RAW) store8(out_raw + off, racc[i][j]);
+      }
+  } else {
+    // input pixel (row_unit, uw) -> outputs (2*row_unit + {0,1}, 2*uw + {0,1})
+    const int Ho = H * 2, Wo = W * 2;
+    float top[3][8], bot[3][8], rtop[3][8], rbot[3][8];
+#pragma unroll
+    for (int cj = 0; cj < 3; ++cj) {
+      float a0[8], a1[8], a2[8], r0[8], r1[8], r2[8];
+      load_act<ACT>(o, H, W, row_unit - 1, uw - 1 + cj, a0, r0, RAW);
+      load_act<ACT>(o, H, W, row_unit, uw - 1 + cj, a1, r1, RAW);
+      load_act<ACT>(o, H, W, row_unit + 1, uw - 1 + cj, a2, r2, RAW);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        top[cj][c] = 0.25f * a0[c] + 0.75f * a1[c];
+        bot[cj][c] = 0.75f * a1[c] + 0.25f * a2[c];
+        if (RAW) {
+          rtop[cj][c] = 0.25f * r0[c] + 0.75f * r1[c];
+          rbot[cj][c] = 0.75f * r1[c] + 0.25f * r2[c];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float e[8], f[8], re[8], rf[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float* l = i ? bot[0] : top[0];
+        const float* m = i ? bot[1] : top[1];
+        const float* r = i ? bot[2] : top[2];
+        e[c] = 0.25f * l[c] + 0.75f * m[c];
+        f[c] = 0.75f * m[c] + 0.25f * r[c];
+        if (RAW) {
+          const float* rl = i ? rbot[0] : rtop[0];
+          const float* rm = i ? rbot[1] : rtop[1];
+          const float* rr = i ? rbot[2] : rtop[2];
+          re[c] = 0.25f * rl[c] + 0.75f * rm[c];
+          rf[c] = 0.75f * rm[c] + 0.25f * rr[c];
+        }
+      }
+      const size_t off = ((static_cast<size_t>(b) * Ho + 2 * row_unit + i) * Wo + 2 * uw) * C + c0;
+      store8(out + off, e);
+      store8(out + off + C, f);
+      if (RAW) {
+        store8(out_raw + off, re);
+        store8(out_raw + off + C, rf);
+      }
+    }
   }
 }
 
@@ -279,16 +371,17 @@ __global__ void pyramid_up_add_kernel(const float4* __restrict__ lo, const float
 }
 
 // ------------------------------------------------------------------------------------------
-// input conv 3x3, 4 -> 64 channels (fp32 math on CUDA cores, K = 36 is too thin for UMMA)
-// block = 32 pixels (along W) x 8 channel-octets; weights [64][4][3][3] staged in smem as
-// [tap*4+ci][64]
+// input conv 3x3, 4 -> 64 channels (fp32 math on CUDA cores: K = 36 is too thin for UMMA and the
+// ODE state stays fp32 on the way in).  Block = 8 warps = 8 channel octets; each lane computes
+// two adjacent pixels x 8 channels so every LDS.128 of weights feeds 8 FMAs.
+// smem weights: [tap][ci][64]
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_in_kernel(const float4* __restrict__ in,
                                                       const float* __restrict__ w,
                                                       const float* __restrict__ bias,
                                                       __nv_bfloat16* __restrict__ out, int B, int H,
                                                       int W) {
-  __shared__ float sw[36][64];
+  __shared__ __align__(16) float sw[36][64];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 64 * 36; i += 256) {
     const int co = i / 36, r = i % 36;      // r = ci*9 + kh*3 + kw   (OIHW)
@@ -298,67 +391,81 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float4* __restrict__
   if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31, o = threadIdx.x >> 5;
-  const int wtiles = (W + 31) / 32;
-  const size_t ntiles = static_cast<size_t>(B) * H * wtiles;
-  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int wt = static_cast<int>(tile % wtiles);
-    const int h = static_cast<int>((tile / wtiles) % H);
-    const int b = static_cast<int>(tile / (static_cast<size_t>(wtiles) * H));
-    const int wx = wt * 32 + lane;
+  const int wtiles = (W + 63) / 64;
+  const int ntiles = B * H * wtiles;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int wt = tile % wtiles;
+    const int h = (tile / wtiles) % H;
+    const int b = tile / (wtiles * H);
+    const int wx = wt * 64 + lane * 2;
     if (wx >= W) continue;
-    float acc[8];
+    float acc0[8], acc1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = sb[o * 8 + i];
+    for (int i = 0; i < 8; ++i) acc0[i] = acc1[i] = sb[o * 8 + i];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int hi = h + kh - 1;
       if (hi < 0 || hi >= H) continue;
+      const float4* rowp = in + (static_cast<size_t>(b) * H + hi) * W;
+      float4 v[4];   // input columns wx-1 .. wx+2
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int wi = wx - 1 + j;
+        v[j] = (wi >= 0 && wi < W) ? rowp[wi] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int wi = wx + kw - 1;
-        if (wi < 0 || wi >= W) continue;
-        const float4 v = in[(static_cast<size_t>(b) * H + hi) * W + wi];
         const int t = kh * 3 + kw;
-        const float* w0 = &sw[t * 4 + 0][o * 8];
-        const float* w1 = &sw[t * 4 + 1][o * 8];
-        const float* w2 = &sw[t * 4 + 2][o * 8];
-        const float* w3 = &sw[t * 4 + 3][o * 8];
+        const float4 x0 = v[kw], x1 = v[kw + 1];
+        const float xin0[4] = {x0.x, x0.y, x0.z, x0.w};
+        const float xin1[4] = {x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[i] = fmaf(v.x, w0[i], acc[i]);
-          acc[i] = fmaf(v.y, w1[i], acc[i]);
-          acc[i] = fmaf(v.z, w2[i], acc[i]);
-          acc[i] = fmaf(v.w, w3[i], acc[i]);
+        for (int ci = 0; ci < 4; ++ci) {
+          const float4 wa = *reinterpret_cast<const float4*>(&sw[t * 4 + ci][o * 8]);
+          const float4 wb = *reinterpret_cast<const float4*>(&sw[t * 4 + ci][o * 8 + 4]);
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc0[i] = fmaf(xin0[ci], wv[i], acc0[i]);
+            acc1[i] = fmaf(xin1[ci], wv[i], acc1[i]);
+          }
         }
       }
     }
-    store8(out + ((static_cast<size_t>(b) * H + h) * W + wx) * 64 + o * 8, acc);
+    __nv_bfloat16* op = out + ((static_cast<size_t>(b) * H + h) * W + wx) * 64 + o * 8;
+    store8(op, acc0);
+    if (wx + 1 < W) store8(op + 64, acc1);
   }
 }
 
 // Combine(method='sum'): out = h + Conv1x1_{4->C}(pyr) + bias   (layerspp.py:62-69)
+// thread = one channel octet (weights held in registers) walking pixels with the block stride
 __global__ void __launch_bounds__(256) combine_kernel(const float4* __restrict__ pyr,
                                                       const float* __restrict__ w,   // [C][4]
                                                       const float* __restrict__ bias,
                                                       const __nv_bfloat16* __restrict__ h,
-                                                      __nv_bfloat16* __restrict__ out, size_t npix,
+                                                      __nv_bfloat16* __restrict__ out, int npix,
                                                       int C) {
   const int oct = C >> 3;
-  const size_t total = npix * oct;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int o = static_cast<int>(idx % oct);
-    const size_t pix = idx / oct;
+  const int o = threadIdx.x % oct;
+  const int pl = threadIdx.x / oct;
+  const int ppb = 256 / oct;          // pixels per block iteration
+  if (pl >= ppb) return;
+  float4 wr[8];
+  float br[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    wr[i] = *reinterpret_cast<const float4*>(w + (o * 8 + i) * 4);
+    br[i] = bias[o * 8 + i];
+  }
+  for (int pix = blockIdx.x * ppb + pl; pix < npix; pix += gridDim.x * ppb) {
     const float4 p = pyr[pix];
     float v[8];
-    load8(h + pix * C + o * 8, v);
+    load8(h + static_cast<size_t>(pix) * C + o * 8, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = o * 8 + i;
-      const float4 wc = *reinterpret_cast<const float4*>(w + c * 4);
-      v[i] += bias[c] + wc.x * p.x + wc.y * p.y + wc.z * p.z + wc.w * p.w;
-    }
-    store8(out + pix * C + o * 8, v);
+    for (int i = 0; i < 8; ++i)
+      v[i] += br[i] + wr[i].x * p.x + wr[i].y * p.y + wr[i].z * p.z + wr[i].w * p.w;
+    store8(out + static_cast<size_t>(pix) * C + o * 8, v);
   }
 }
 
@@ -459,38 +566,47 @@ extern "C" int fd_chan_stats(const void* x, int B, int HW, int C, float* partial
   return check_launch("fd_chan_stats");
 }
 
-extern "C" int fd_gn_finalize(const float* part1, int C1, const float* part2, int C2, int S, int B,
-                              double count, const float* gamma, const float* beta, int groups,
+extern "C" int fd_gn_finalize(const float* part1, int C1, int S1, const float* part2, int C2, int S2,
+                              int B, double count, const float* gamma, const float* beta, int groups,
                               float eps, float* scale_shift, cudaStream_t stream) {
   FD_REQUIRE((C1 + C2) % groups == 0, "fd_gn_finalize: C=%d not divisible by groups=%d", C1 + C2, groups);
-  gn_finalize_kernel<<<dim3(groups, B), 128, 0, stream>>>(part1, C1, part2, C2, S, count, gamma, beta,
-                                                          groups, eps, scale_shift);
+  gn_finalize_kernel<<<dim3(groups, B), 128, 0, stream>>>(part1, C1, S1, part2, C2, S2, count, gamma,
+                                                          beta, groups, eps, scale_shift);
   return check_launch("fd_gn_finalize");
 }
 
 extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, int C2,
-                                  const float* scale_shift, void* out, int B, int H, int W, int mode,
-                                  int apply_act, cudaStream_t stream) {
+                                  const float* scale_shift, void* out, void* out_raw, int B, int H,
+                                  int W, int mode, cudaStream_t stream) {
   FD_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0, "fd_gn_act_resample: channels must be multiples of 8");
   FD_REQUIRE(mode >= 0 && mode <= 2, "fd_gn_act_resample: mode %d", mode);
-  FD_REQUIRE(mode != 1 || (H % 2 == 0 && W % 2 == 0), "fd_gn_act_resample: odd size for down-sampling");
-  const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H);
-  const int Wo = mode == 1 ? W / 2 : (mode == 2 ? W * 2 : W);
-  const size_t total = static_cast<size_t>(B) * Ho * Wo * ((C1 + C2) / 8);
-  const int grid = grid_for(total, 256);
+  FD_REQUIRE(mode != 1 || (H % 4 == 0 && W % 4 == 0), "fd_gn_act_resample: down-sampling needs H, W % 4 == 0");
+  FD_REQUIRE(out != nullptr || out_raw != nullptr, "fd_gn_act_resample: no output");
+  FD_REQUIRE(out == nullptr || scale_shift != nullptr, "fd_gn_act_resample: activated output needs scale_shift");
+  FD_REQUIRE(mode != 0 || out != nullptr, "fd_gn_act_resample: mode 0 without activation is a copy");
+  const int oct = (C1 + C2) / 8;
+  const int UW = mode == 1 ? W / 4 : W;
+  const int UH = mode == 1 ? H / 4 : H;
+  FD_REQUIRE(static_cast<long long>(B) * UH <= 65535, "fd_gn_act_resample: B*rows=%lld exceeds grid.y",
+             static_cast<long long>(B) * UH);
+  dim3 grid((UW * oct + 255) / 256, B * UH);
   const bf16* s1 = static_cast<const bf16*>(src1);
   const bf16* s2 = static_cast<const bf16*>(src2);
   bf16* o = static_cast<bf16*>(out);
-#define FD_LAUNCH_GN(M, A) \
-  gn_act_resample_kernel<M, A><<<grid, 256, 0, stream>>>(s1, C1, s2, C2, scale_shift, o, B, H, W)
-  if (apply_act) {
-    if (mode == 0) FD_LAUNCH_GN(0, true);
-    else if (mode == 1) FD_LAUNCH_GN(1, true);
-    else FD_LAUNCH_GN(2, true);
+  bf16* r = static_cast<bf16*>(out_raw);
+#define FD_LAUNCH_GN(M, A, R) \
+  gn_act_resample_kernel<M, A, R><<<grid, 256, 0, stream>>>(s1, C1, s2, C2, scale_shift, A ? o : r, r, H, W)
+  if (o != nullptr && r != nullptr) {
+    if (mode == 1) FD_LAUNCH_GN(1, true, true);
+    else if (mode == 2) FD_LAUNCH_GN(2, true, true);
+    else FD_REQUIRE(false, "fd_gn_act_resample: raw output only with resampling modes");
+  } else if (o != nullptr) {
+    if (mode == 0) FD_LAUNCH_GN(0, true, false);
+    else if (mode == 1) FD_LAUNCH_GN(1, true, false);
+    else FD_LAUNCH_GN(2, true, false);
   } else {
-    if (mode == 0) FD_LAUNCH_GN(0, false);
-    else if (mode == 1) FD_LAUNCH_GN(1, false);
-    else FD_LAUNCH_GN(2, false);
+    if (mode == 1) FD_LAUNCH_GN(1, false, false);
+    else FD_LAUNCH_GN(2, false, false);
   }
 #undef FD_LAUNCH_GN
   return check_launch("fd_gn_act_resample");
@@ -520,7 +636,8 @@ extern "C" int fd_pyramid_up_add(const void* lo, const void* add, void* out, int
 
 extern "C" int fd_conv_in(const void* in4, const float* w, const float* bias, void* out, int B, int H,
                           int W, cudaStream_t stream) {
-  const size_t ntiles = static_cast<size_t>(B) * H * ((W + 31) / 32);
+  const size_t ntiles = static_cast<size_t>(B) * H * ((W + 63) / 64);
+  FD_REQUIRE(ntiles < (1u << 31), "fd_conv_in: too many tiles");
   const int grid = static_cast<int>(ntiles < 148 * 8 ? ntiles : 148 * 8);
   conv_in_kernel<<<grid, 256, 0, stream>>>(static_cast<const float4*>(in4), w, bias,
                                            static_cast<bf16*>(out), B, H, W);
@@ -530,9 +647,11 @@ extern "C" int fd_conv_in(const void* in4, const float* w, const float* bias, vo
 extern "C" int fd_combine(const void* pyr4, const float* w, const float* bias, const void* h, void* out,
                           size_t npix, int C, cudaStream_t stream) {
   FD_REQUIRE(C % 8 == 0, "fd_combine: C=%d", C);
-  combine_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, stream>>>(
+  FD_REQUIRE(C <= 2048 && npix < (1u << 31), "fd_combine: C=%d / npix out of range", C);
+  const int ppb = 256 / (C / 8);
+  combine_kernel<<<grid_for((npix + ppb - 1) / ppb, 1), 256, 0, stream>>>(
       static_cast<const float4*>(pyr4), w, bias, static_cast<const bf16*>(h), static_cast<bf16*>(out),
-      npix, C);
+      static_cast<int>(npix), C);
   return check_launch("fd_combine");
 }
 

@@ -33,7 +33,12 @@ def pack_conv_weight(segments, npad):
     return wp.contiguous()
 
 
-def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None):
+def conv_stats_slabs(H, W):
+    """number of partial-sum slabs the conv epilogue writes per sample (4 warps x 128-pixel tiles)"""
+    return 4 * (H * W // 128)
+
+
+def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None):
     """srcs: list of (tensor NHWC bf16, c_begin, c_count, taps). out: NHWC bf16 [.., npad] or fp32 [.., cout<=16]."""
     L = _lib.lib()
     n = len(srcs)
@@ -52,7 +57,8 @@ def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     rc = L.fd_conv2d_igemm(arr, n, _lib.ptr(wpacked), ktot, _lib.ptr(bias), _lib.ptr(out),
-                           int(out_f32), out.shape[3], npad, B, H, W, max_ctas, _lib.stream_ptr())
+                           int(out_f32), out.shape[3], npad, B, H, W, _lib.ptr(stats), max_ctas,
+                           _lib.stream_ptr())
     _lib.check(rc, "fd_conv2d_igemm")
     if PROFILE is not None:
         e1.record()
@@ -79,26 +85,28 @@ def chan_stats(x, slabs, out=None):
 
 
 def gn_finalize(parts, chans, count, gamma, beta, groups, eps, out):
-    """parts: 1 or 2 partial-sum tensors [B,S,Ci,2] forming the virtual concat. out: fp32 [B,C,2]."""
+    """parts: 1 or 2 partial-sum tensors [B,Si,Ci,2] forming the virtual concat. out: fp32 [B,C,2]."""
     p1 = parts[0]
     p2 = parts[1] if len(parts) > 1 else None
     c2 = chans[1] if len(parts) > 1 else 0
-    B, S = p1.shape[0], p1.shape[1]
-    rc = _lib.lib().fd_gn_finalize(_lib.ptr(p1), chans[0], _lib.ptr(p2), c2, S, B, ctypes.c_double(count),
-                                   _lib.ptr(gamma), _lib.ptr(beta), groups, ctypes.c_float(eps),
-                                   _lib.ptr(out), _lib.stream_ptr())
+    s2 = p2.shape[1] if p2 is not None else 0
+    B = p1.shape[0]
+    rc = _lib.lib().fd_gn_finalize(_lib.ptr(p1), chans[0], p1.shape[1], _lib.ptr(p2), c2, s2, B,
+                                   ctypes.c_double(count), _lib.ptr(gamma), _lib.ptr(beta), groups,
+                                   ctypes.c_float(eps), _lib.ptr(out), _lib.stream_ptr())
     _lib.check(rc, "fd_gn_finalize")
     return out
 
 
-def gn_act_resample(srcs, scale_shift, out, mode, act):
-    """srcs: 1 or 2 bf16 NHWC tensors (virtual concat). mode 0/1/2 = same/down/up."""
+def gn_act_resample(srcs, scale_shift, out, mode, out_raw=None):
+    """srcs: 1 or 2 bf16 NHWC tensors (virtual concat). mode 0/1/2 = same/down/up.
+    out: SiLU(GroupNorm) output (or None); out_raw: FIR of the raw input (or None)."""
     s1 = srcs[0]
     s2 = srcs[1] if len(srcs) > 1 else None
     B, H, W, C1 = s1.shape
     C2 = s2.shape[3] if s2 is not None else 0
     rc = _lib.lib().fd_gn_act_resample(_lib.ptr(s1), C1, _lib.ptr(s2), C2, _lib.ptr(scale_shift),
-                                       _lib.ptr(out), B, H, W, mode, int(act), _lib.stream_ptr())
+                                       _lib.ptr(out), _lib.ptr(out_raw), B, H, W, mode, _lib.stream_ptr())
     _lib.check(rc, "fd_gn_act_resample")
     return out
 

@@ -46,10 +46,13 @@ struct fd_conv_src {
  * out_is_f32 = 0: out bf16 NHWC [B,H,W,cout], cout == npad in {128,256}
  * out_is_f32 = 1: out fp32 NHWC [B,H,W,cout], cout <= 16, npad == 16 (the 4-channel pyramid convs)
  * bias: fp32 [npad] or NULL.  Requires W % 8 == 0 and H % (128 / min(128, pow2 divisor of W)) == 0.
+ * stats (bf16 output only, may be NULL): GroupNorm partial sums of the OUTPUT, fp32
+ * [B, S, cout, 2] with S = 4 * H*W/128 slabs (one per epilogue warp and tile), consumed by
+ * fd_gn_finalize — the statistics pass of the next GroupNorm fused into this conv's epilogue.
  * max_ctas: 0 = one persistent CTA per SM. */
 int fd_conv2d_igemm(const struct fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot,
                     const float* bias, void* out, int out_is_f32, int cout, int npad, int B, int H,
-                    int W, int max_ctas, fd_stream_t stream);
+                    int W, float* stats, int max_ctas, fd_stream_t stream);
 
 /* ---- GroupNorm + SiLU + FIR resampling ------------------------------------------------------
  * replace nn.GroupNorm / nn.SiLU (layerspp.py:229,241,253,274; ncsnpp.py:216,228) and
@@ -57,16 +60,17 @@ int fd_conv2d_igemm(const struct fd_conv_src* srcs, int nsrc, const void* wpacke
  * op/upfirdn2d.cpp:38-48, op/upfirdn2d_kernel.cu:118-218). */
 /* partial[b][s][c][0..1] = sum / sum of squares of x over slab s of the HW pixels (S slabs) */
 int fd_chan_stats(const void* x_bf16, int B, int HW, int C, float* partial, int S, fd_stream_t stream);
-/* group statistics over the virtual channel concat [part1 (C1), part2 (C2)] (fp64 reduction) ->
+/* group statistics over the virtual channel concat [part1 [B,S1,C1,2], part2 [B,S2,C2,2]] (fp64) ->
  * scale_shift fp32 [B, C1+C2, 2]:  y = x * scale + shift == GroupNorm(x) with gamma/beta */
-int fd_gn_finalize(const float* part1, int C1, const float* part2, int C2, int S, int B, double count,
-                   const float* gamma, const float* beta, int groups, float eps, float* scale_shift,
-                   fd_stream_t stream);
-/* out = FIR_mode( apply_act ? SiLU(x*scale+shift) : x ) over the virtual concat [src1, src2];
- * mode 0 none, 1 down x2 ([1,3,3,1]/8 per axis, pad (1,1)), 2 up x2 ([1,3,3,1]/4, pad (2,1));
- * out bf16 NHWC [B,H',W',C1+C2] */
+int fd_gn_finalize(const float* part1, int C1, int S1, const float* part2, int C2, int S2, int B,
+                   double count, const float* gamma, const float* beta, int groups, float eps,
+                   float* scale_shift, fd_stream_t stream);
+/* act = FIR_mode(SiLU(x*scale+shift)) -> out, and/or raw = FIR_mode(x) -> out_raw (the res-block's
+ * resampled skip input, layerspp.py:257-268), over the virtual concat [src1, src2]; either output
+ * may be NULL.  mode 0 none (activated output only), 1 down x2 ([1,3,3,1]/8 per axis, pad (1,1)),
+ * 2 up x2 ([1,3,3,1]/4, pad (2,1)); outputs bf16 NHWC [B,H',W',C1+C2] */
 int fd_gn_act_resample(const void* src1, int C1, const void* src2, int C2, const float* scale_shift,
-                       void* out, int B, int H, int W, int mode, int apply_act, fd_stream_t stream);
+                       void* out, void* out_raw, int B, int H, int W, int mode, fd_stream_t stream);
 
 /* ---- 4-channel paths of NCSN++ ---------------------------------------------------------------*/
 /* ncsnpp.py:261,401-404: (re x, im x, re y, im y) -> fp32 [npix,4] */
