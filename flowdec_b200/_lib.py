@@ -39,6 +39,7 @@ SIGNATURES = {
     "fd_abi_version": [],
     "fd_conv2d_igemm": [ctypes.POINTER(ConvSrc), _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
     "fd_chan_stats": [_P, _I, _I, _I, _P, _I, _P],
+    "fd_slab_reduce": [_P, _I, _I, _I, _P, _I, _P],
     "fd_gn_finalize": [_P, _I, _I, _P, _I, _I, _I, _D, _P, _P, _I, _F, _P, _P],
     "fd_gn_act_resample": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "fd_pack4": [_P, _P, _P, _Z, _P],

@@ -347,8 +347,9 @@ class NCSNpp(nn.Module):
         st_h1 = None
         if self.fuse_stats:
             st_h1 = self._ws.get("h1_stats", (B, ops.conv_stats_slabs(Ho, Wo), cout, 2), torch.float32, dev)
-            scache[h1.data_ptr()] = st_h1
         ops.conv_igemm([(a0, 0, cin, 9)], e["w0"], tb[i], h1, self.max_ctas, stats=st_h1)
+        if st_h1 is not None:
+            scache[h1.data_ptr()] = self._compact_stats(st_h1, "h1_stats_c")
         a1 = self._gn_act([h1], e["g1"], e["be1"], 0, scache, "act")
         scache.pop(h1.data_ptr(), None)
         if mode != 0:
@@ -361,11 +362,23 @@ class NCSNpp(nn.Module):
         scache.pop(out.data_ptr(), None)
         st_out = None
         if self.fuse_stats and want_stats:
-            st_out = self._ws.get(f"rb{i}_stats", (B, ops.conv_stats_slabs(Ho, Wo), cout, 2), torch.float32, dev)
-            scache[out.data_ptr()] = st_out
+            S = ops.conv_stats_slabs(Ho, Wo)
+            # large S: shared scratch, compacted below into a per-block buffer; small S: kept as is
+            st_out = self._ws.get("rb_stats" if S > self.stats_slabs else f"rb{i}_stats_c", (B, S, cout, 2),
+                                  torch.float32, dev)
         ops.conv_igemm([(a1, 0, cout, 9)] + [(s, 0, s.shape[3], 1) for s in skip], wp, e["b1"], out,
                        self.max_ctas, algo_k=algo_k, stats=st_out)
+        if st_out is not None:
+            scache[out.data_ptr()] = self._compact_stats(st_out, f"rb{i}_stats_c")
         return out
+
+    def _compact_stats(self, st, name):
+        """conv-epilogue partials [B,S,C,2] -> at most `stats_slabs` slabs (coalesced stage-1 reduce)"""
+        B, S, C, _ = st.shape
+        if S <= self.stats_slabs:
+            return st
+        out = self._ws.get(name, (B, self.stats_slabs, C, 2), torch.float32, st.device)
+        return ops.slab_reduce(st, self.stats_slabs, out)
 
     # ------------------------------------------------------------------ forward
     def velocity(self, x, y, t, out=None, base1=None, c1=0.0, base2=None, c2=0.0, coef=1.0, v_out=None):

@@ -83,6 +83,33 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const __nv_bfloat16* __
   }
 }
 
+// stage 1 of the statistics reduction when a producer wrote many slabs (the conv epilogue writes
+// one per warp and tile): block (chunk, b) sums `per` consecutive slabs for all channels with fully
+// coalesced row reads; fp32 pairwise over <= a few hundred terms, fixed order.
+__global__ void __launch_bounds__(256) slab_reduce_kernel(const float* __restrict__ in, int S, int C2x,
+                                                          float* __restrict__ out, int chunks) {
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int per = (S + chunks - 1) / chunks;
+  const int s0 = chunk * per, s1 = min(S, s0 + per);
+  for (int i = threadIdx.x; i < C2x; i += 256) {
+    const float* p = in + (static_cast<size_t>(b) * S + s0) * C2x + i;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int sl = s0;
+    for (; sl + 3 < s1; sl += 4) {
+      a0 += p[0];
+      a1 += p[C2x];
+      a2 += p[2 * static_cast<size_t>(C2x)];
+      a3 += p[3 * static_cast<size_t>(C2x)];
+      p += 4 * static_cast<size_t>(C2x);
+    }
+    for (; sl < s1; ++sl) {
+      a0 += p[0];
+      p += C2x;
+    }
+    out[(static_cast<size_t>(b) * chunks + chunk) * C2x + i] = (a0 + a1) + (a2 + a3);
+  }
+}
+
 // one block per (group, sample): mean / rstd over the group's channels of the virtual concat
 // [src1 (C1 channels), src2 (C2 channels)], then per-channel scale/shift.
 __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part1, int C1, int S1,
@@ -147,7 +174,7 @@ struct Oct {
   float sc[8], sh[8];
 };
 
-template <bool ACT>
+template <bool ACT, bool FAST = true>
 __device__ __forceinline__ void load_act(const Oct& o, int H, int W, int hi, int wi, float (&a)[8],
                                          float (&r)[8], bool want_raw) {
   if (hi < 0 || hi >= H || wi < 0 || wi >= W) {
@@ -160,7 +187,7 @@ __device__ __forceinline__ void load_act(const Oct& o, int H, int W, int hi, int
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (want_raw) r[i] = v[i];
-    a[i] = ACT ? silu_f(fmaf(v[i], o.sc[i], o.sh[i])) : v[i];
+    a[i] = ACT ? (FAST ? silu_fast(fmaf(v[i], o.sc[i], o.sh[i])) : silu_f(fmaf(v[i], o.sc[i], o.sh[i]))) : v[i];
   }
 }
 
@@ -196,9 +223,7 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
     }
   }
   if (MODE == 0) {
-    float a[8], r[8];
-    load_act<ACT>(o, H, W, row_unit, uw, a, r, false);
-    store8(out + ((static_cast<size_t>(b) * H + row_unit) * W + uw) * C + c0, a);
+    // handled by gn_act_kernel (several pixels per thread, scale/shift held in registers)
   } else if (MODE == 1) {
     // outputs (2*row_unit + {0,1}, 2*uw + {0,1}); inputs rows 4*row_unit-1 .. +4, cols 4*uw-1 .. +4
     const int Ho = H / 2, Wo = W / 2;
@@ -294,6 +319,53 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
         store8(out_raw + off + C, rf);
       }
     }
+  }
+}
+
+// MODE 0 specialisation: a = SiLU(x*scale+shift), same resolution.  A thread owns one channel
+// octet (scale/shift in registers) and walks kPix pixels spaced one block-row apart, so the 64 B
+// of per-channel parameters are loaded once per 8 x 16 B of activations.
+template <int kPix>
+__global__ void __launch_bounds__(256) gn_act_kernel(const __nv_bfloat16* __restrict__ src1, int C1,
+                                                     const __nv_bfloat16* __restrict__ src2, int C2,
+                                                     const float* __restrict__ scale_shift,
+                                                     __nv_bfloat16* __restrict__ out, int HW) {
+  const int C = C1 + C2;
+  const int oct = C >> 3;
+  const int ppb = 256 / oct;               // pixels covered by one block pass
+  const int o8 = threadIdx.x % oct;
+  const int pl = threadIdx.x / oct;
+  if (pl >= ppb) return;
+  const int b = blockIdx.y;
+  const int c0 = o8 * 8;
+  const bool first = c0 < C1;
+  const int Cs = first ? C1 : C2;
+  const __nv_bfloat16* img = (first ? src1 : src2) + static_cast<size_t>(b) * HW * Cs + (first ? c0 : c0 - C1);
+  float sc[8], sh[8];
+  const float4* ss = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(b) * C + c0) * 2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 q = ss[i];
+    sc[2 * i] = q.x; sh[2 * i] = q.y; sc[2 * i + 1] = q.z; sh[2 * i + 1] = q.w;
+  }
+  const int p0 = blockIdx.x * (ppb * kPix) + pl;
+  uint4 raw[kPix];
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    const int p = p0 + j * ppb;
+    if (p < HW) raw[j] = *reinterpret_cast<const uint4*>(img + static_cast<size_t>(p) * Cs);
+  }
+  __nv_bfloat16* ob = out + static_cast<size_t>(b) * HW * C + c0;
+#pragma unroll
+  for (int j = 0; j < kPix; ++j) {
+    const int p = p0 + j * ppb;
+    if (p >= HW) continue;
+    const float2 a = unpack_bf16x2(raw[j].x), bq = unpack_bf16x2(raw[j].y), c = unpack_bf16x2(raw[j].z),
+                 d = unpack_bf16x2(raw[j].w);
+    float v[8] = {a.x, a.y, bq.x, bq.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = silu_f(fmaf(v[i], sc[i], sh[i]));
+    store8(ob + static_cast<size_t>(p) * C, v);
   }
 }
 
@@ -566,6 +638,13 @@ extern "C" int fd_chan_stats(const void* x, int B, int HW, int C, float* partial
   return check_launch("fd_chan_stats");
 }
 
+extern "C" int fd_slab_reduce(const float* in, int B, int S, int C, float* out, int chunks,
+                              cudaStream_t stream) {
+  FD_REQUIRE(chunks >= 1 && chunks <= S, "fd_slab_reduce: chunks=%d out of range for S=%d", chunks, S);
+  slab_reduce_kernel<<<dim3(chunks, B), 256, 0, stream>>>(in, S, C * 2, out, chunks);
+  return check_launch("fd_slab_reduce");
+}
+
 extern "C" int fd_gn_finalize(const float* part1, int C1, int S1, const float* part2, int C2, int S2,
                               int B, double count, const float* gamma, const float* beta, int groups,
                               float eps, float* scale_shift, cudaStream_t stream) {
@@ -587,8 +666,8 @@ extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, in
   const int oct = (C1 + C2) / 8;
   const int UW = mode == 1 ? W / 4 : W;
   const int UH = mode == 1 ? H / 4 : H;
-  FD_REQUIRE(static_cast<long long>(B) * UH <= 65535, "fd_gn_act_resample: B*rows=%lld exceeds grid.y",
-             static_cast<long long>(B) * UH);
+  FD_REQUIRE(static_cast<long long>(B) * UH <= 65535 && oct <= 256,
+             "fd_gn_act_resample: B*rows=%lld exceeds grid.y (or C > 2048)", static_cast<long long>(B) * UH);
   dim3 grid((UW * oct + 255) / 256, B * UH);
   const bf16* s1 = static_cast<const bf16*>(src1);
   const bf16* s2 = static_cast<const bf16*>(src2);
@@ -601,8 +680,12 @@ extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, in
     else if (mode == 2) FD_LAUNCH_GN(2, true, true);
     else FD_REQUIRE(false, "fd_gn_act_resample: raw output only with resampling modes");
   } else if (o != nullptr) {
-    if (mode == 0) FD_LAUNCH_GN(0, true, false);
-    else if (mode == 1) FD_LAUNCH_GN(1, true, false);
+    if (mode == 0) {
+      const int ppb = 256 / oct;
+      constexpr int kPix = 8;
+      dim3 g0((H * W + ppb * kPix - 1) / (ppb * kPix), B);
+      gn_act_kernel<kPix><<<g0, 256, 0, stream>>>(s1, C1, s2, C2, scale_shift, o, H * W);
+    } else if (mode == 1) FD_LAUNCH_GN(1, true, false);
     else FD_LAUNCH_GN(2, true, false);
   } else {
     if (mode == 1) FD_LAUNCH_GN(1, false, false);

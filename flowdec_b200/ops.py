@@ -84,6 +84,14 @@ def chan_stats(x, slabs, out=None):
     return out
 
 
+def slab_reduce(part, chunks, out):
+    """part fp32 [B,S,C,2] -> out fp32 [B,chunks,C,2]"""
+    B, S, C, _ = part.shape
+    _lib.check(_lib.lib().fd_slab_reduce(_lib.ptr(part), B, S, C, _lib.ptr(out), chunks, _lib.stream_ptr()),
+               "fd_slab_reduce")
+    return out
+
+
 def gn_finalize(parts, chans, count, gamma, beta, groups, eps, out):
     """parts: 1 or 2 partial-sum tensors [B,Si,Ci,2] forming the virtual concat. out: fp32 [B,C,2]."""
     p1 = parts[0]

@@ -60,6 +60,8 @@ int fd_conv2d_igemm(const struct fd_conv_src* srcs, int nsrc, const void* wpacke
  * op/upfirdn2d.cpp:38-48, op/upfirdn2d_kernel.cu:118-218). */
 /* partial[b][s][c][0..1] = sum / sum of squares of x over slab s of the HW pixels (S slabs) */
 int fd_chan_stats(const void* x_bf16, int B, int HW, int C, float* partial, int S, fd_stream_t stream);
+/* out[b][chunk][c][2] = sum over the chunk's slabs of in[b][s][c][2] (stage 1 when S is large) */
+int fd_slab_reduce(const float* in, int B, int S, int C, float* out, int chunks, fd_stream_t stream);
 /* group statistics over the virtual channel concat [part1 [B,S1,C1,2], part2 [B,S2,C2,2]] (fp64) ->
  * scale_shift fp32 [B, C1+C2, 2]:  y = x * scale + shift == GroupNorm(x) with gamma/beta */
 int fd_gn_finalize(const float* part1, int C1, int S1, const float* part2, int C2, int S2, int B,
