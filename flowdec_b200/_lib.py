@@ -37,7 +37,7 @@ _Z = ctypes.c_size_t
 # One entry per `extern "C"` function declared in include/flowdec_b200.h (same order).
 SIGNATURES = {
     "fd_abi_version": [],
-    "fd_conv2d_igemm": [ctypes.POINTER(ConvSrc), _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
+    "fd_conv2d_igemm": [ctypes.POINTER(ConvSrc), _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P],
     "fd_chan_stats": [_P, _I, _I, _I, _P, _I, _P],
     "fd_slab_reduce": [_P, _I, _I, _I, _P, _I, _P],
     "fd_gn_finalize": [_P, _I, _I, _P, _I, _I, _I, _D, _P, _P, _I, _F, _P, _P],

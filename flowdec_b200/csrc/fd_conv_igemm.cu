@@ -52,10 +52,12 @@ struct ConvParams {
   int cout_valid;
 };
 
-template <int N>
+template <int N, bool CTA2 = false>
 struct ConvCfg {
-  static constexpr int kStages = (N == 256) ? 4 : (N == 128 ? 6 : 8);
-  static constexpr int kBBytes = N * kSliceK * 2;
+  // B rows held by one CTA: the pair splits the N weight rows between its two shared memories
+  static constexpr int kBRows = CTA2 ? N / 2 : N;
+  static constexpr int kBBytes = kBRows * kSliceK * 2;
+  static constexpr int kStages = (N == 256) ? (CTA2 ? 6 : 4) : (N == 128 ? (CTA2 ? 8 : 6) : 8);
   static constexpr int kOutBytes = (N >= 64) ? 2 * kTileM * 128 : 0;  // two 64-channel staging tiles
   static constexpr int kTmemCols = (2 * N <= 32) ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes =
@@ -107,9 +109,10 @@ __device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], const flo
   }
 }
 
-template <int N, bool OUT_F32>
+template <int N, bool OUT_F32, bool CTA2>
 __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<N>;
+  using Cfg = ConvCfg<N, CTA2>;
+  static_assert(!(CTA2 && OUT_F32), "the CTA-pair variant is instantiated for the bf16-output tiles only");
   constexpr int STAGES = Cfg::kStages;
   constexpr int B_BYTES = Cfg::kBBytes;
 
@@ -132,25 +135,37 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
 
   for (int i = threadIdx.x; i < N; i += blockDim.x) sBias[i] = p.bias ? p.bias[i] : 0.0f;
 
+  // CTA pair: rank 0 (leader) issues the MMAs; its full / tmem-empty barriers collect the
+  // arrivals of both CTAs, the empty / tmem-full barriers of both CTAs are signalled by multicast.
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader_cta = (rank == 0);
+  constexpr uint32_t kPair = CTA2 ? 2u : 1u;
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], kPair);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
+      mbar_init(&tempty_bar[a], 128 * kPair);
     }
     fence_mbar_init();
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.a_map[s]);
     tma_prefetch_desc(&p.b_map);
     if (!OUT_F32) tma_prefetch_desc(&p.out_map);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) {
+    if (CTA2) tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // tile walk: a pair takes two consecutive tiles per step (rank r -> tile 2*step + r)
+  const int tile_first = CTA2 ? static_cast<int>((blockIdx.x >> 1) * 2 + rank) : static_cast<int>(blockIdx.x);
+  const int tile_stride = static_cast<int>(gridDim.x);
 
   int k_iters = 0;
   for (int s = 0; s < p.nseg; ++s) k_iters += p.seg_kslices[s] * p.seg_taps[s];
@@ -161,7 +176,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
         const int n = tile / tiles_per_img;
         const int rem = tile - n * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.bh;
@@ -175,10 +190,19 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
             const int dw = (taps == 9) ? (t % 3 - 1) : 0;
             for (int ks = 0; ks < ksl; ++ks) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
-              mbar_expect_tx(&full_bar[stage], kABytes + B_BYTES);
-              tma_load_4d(sA + stage * kABytes, &p.a_map[s], &full_bar[stage], ks * kSliceK,
-                          w0 + dw, h0 + dh, n);
-              tma_load_2d(sB + stage * B_BYTES, &p.b_map, &full_bar[stage], kb * kSliceK, 0);
+              if (CTA2) {
+                if (leader_cta) mbar_expect_tx(&full_bar[stage], 2 * (kABytes + B_BYTES));
+                else mbar_arrive_remote(&full_bar[stage], 0);
+                tma_load_4d_2sm(sA + stage * kABytes, &p.a_map[s], &full_bar[stage], ks * kSliceK,
+                                w0 + dw, h0 + dh, n);
+                tma_load_2d_2sm(sB + stage * B_BYTES, &p.b_map, &full_bar[stage], kb * kSliceK,
+                                static_cast<int>(rank) * Cfg::kBRows);
+              } else {
+                mbar_expect_tx(&full_bar[stage], kABytes + B_BYTES);
+                tma_load_4d(sA + stage * kABytes, &p.a_map[s], &full_bar[stage], ks * kSliceK,
+                            w0 + dw, h0 + dh, n);
+                tma_load_2d(sB + stage * B_BYTES, &p.b_map, &full_bar[stage], kb * kSliceK, 0);
+              }
               ++kb;
               if (++stage == STAGES) {
                 stage = 0;
@@ -191,13 +215,15 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, N);
+    if (lane == 0 && leader_cta) {
+      constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * kTileM : kTileM, N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int issued = 0;
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
+        ++issued;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * N);
@@ -209,18 +235,27 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
 #pragma unroll
           for (int k = 0; k < kSliceK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128-byte swizzle span (encoded >>4)
-            umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                      idesc, static_cast<uint32_t>((ki | k) != 0));
+            if (CTA2)
+              umma_bf16_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                            idesc, static_cast<uint32_t>((ki | k) != 0));
+            else
+              umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                        idesc, static_cast<uint32_t>((ki | k) != 0));
           }
-          umma_commit(&empty_bar[stage]);
+          if (CTA2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (CTA2) umma_commit_2sm(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
+      }
+      if (CTA2 && issued > 0) {
+        // the peer's epilogue arrives remotely on these barriers: drain them before tear-down
+        for (int j = (issued >= 2 ? issued - 2 : issued - 1); j < issued; ++j)
+          mbar_wait(&tempty_bar[j & 1], static_cast<uint32_t>((j >> 1) & 1));
       }
     }
   } else {
@@ -230,7 +265,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     const bool leader = (threadIdx.x == 64);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * p.bh;
@@ -244,7 +279,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         tmem_ld_32x32b_x16(t_row, v);
         tmem_ld_wait();
         tc_fence_before_sync();
-        mbar_arrive(&tempty_bar[acc]);
+        mbar_arrive(&tempty_bar[acc]);   // OUT_F32 is single-CTA only
         const int hl = row / p.bw;
         const int wl = row - hl * p.bw;
         const size_t pix = (static_cast<size_t>(n) * p.H + (h0 + hl)) * p.W + (w0 + wl);
@@ -274,7 +309,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           tmem_ld_wait();
           if (ch == kChunks - 1) {
             tc_fence_before_sync();
-            mbar_arrive(&tempty_bar[acc]);
+            if (CTA2) mbar_arrive_remote(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
           }
           uint8_t* stg = sOut + (ch & 1) * (kTileM * 128);
           // the TMA store that last read this staging tile must have drained it
@@ -300,8 +335,11 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
 
   __syncwarp();
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (CTA2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if (CTA2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -358,12 +396,12 @@ static int make_nhwc_map(CUtensorMap* m, const void* base, int B, int H, int W, 
   return 0;
 }
 
-static int make_weight_map(CUtensorMap* m, const void* base, int npad, int ktot) {
+static int make_weight_map(CUtensorMap* m, const void* base, int npad, int ktot, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(npad)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kSliceK), static_cast<cuuint32_t>(npad)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kSliceK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -372,19 +410,34 @@ static int make_weight_map(CUtensorMap* m, const void* base, int npad, int ktot)
   return 0;
 }
 
-template <int N, bool OUT_F32>
+template <int N, bool OUT_F32, bool CTA2>
 static int launch_conv(const ConvParams& p, int max_ctas, cudaStream_t stream) {
-  auto kern = conv_igemm_kernel<N, OUT_F32>;
+  auto kern = conv_igemm_kernel<N, OUT_F32, CTA2>;
+  using Cfg = ConvCfg<N, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ConvCfg<N>::kSmemBytes);
-    FD_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", ConvCfg<N>::kSmemBytes,
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    FD_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
                cudaGetErrorString(e));
     attr_set = true;
   }
   int grid = std::min(p.num_tiles, max_ctas > 0 ? max_ctas : device_sm_count());
-  kern<<<grid, 192, ConvCfg<N>::kSmemBytes, stream>>>(p);
+  if (CTA2) grid &= ~1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  FD_REQUIRE(e == cudaSuccess, "fd_conv2d_igemm: launch failed: %s", cudaGetErrorString(e));
   return check_launch("fd_conv2d_igemm");
 }
 
@@ -403,7 +456,7 @@ struct fd_conv_src {
 
 extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot,
                                const float* bias, void* out, int out_is_f32, int cout, int npad,
-                               int B, int H, int W, float* stats, int max_ctas, cudaStream_t stream) {
+                               int B, int H, int W, float* stats, int max_ctas, int cta_pairs, cudaStream_t stream) {
   using namespace fd;
   FD_REQUIRE(nsrc >= 1 && nsrc <= kMaxSeg, "fd_conv2d_igemm: nsrc=%d out of range [1,%d]", nsrc, kMaxSeg);
   FD_REQUIRE(npad == 16 || npad == 128 || npad == 256, "fd_conv2d_igemm: npad=%d unsupported", npad);
@@ -429,7 +482,10 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
       return 1;
   }
   FD_REQUIRE(ksum == ktot, "fd_conv2d_igemm: packed K=%d does not match segments (%d)", ktot, ksum);
-  if (make_weight_map(&p.b_map, wpacked, npad, ktot)) return 1;
+  // CTA pairs (cta_group::2, M = 256 per MMA) for the bf16-output tiles when the tile count is even
+  const bool pair = !out_is_f32 && (cta_pairs != 0) && (((B * (H / bh) * (W / bw)) & 1) == 0) &&
+                    (B * (H / bh) * (W / bw) >= 2);
+  if (make_weight_map(&p.b_map, wpacked, npad, ktot, pair ? npad / 2 : npad)) return 1;
   p.B = B;
   p.H = H;
   p.W = W;
@@ -445,10 +501,12 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
     FD_REQUIRE(stats == nullptr, "fd_conv2d_igemm: stats are produced by the bf16-output kernels only");
     FD_REQUIRE(npad == 16 && cout >= 1 && cout <= 16, "fd_conv2d_igemm: fp32 output needs npad=16");
     p.out_f32 = static_cast<float*>(out);
-    return launch_conv<16, true>(p, max_ctas, stream);
+    return launch_conv<16, true, false>(p, max_ctas, stream);
   }
   FD_REQUIRE(cout == npad && npad >= 128, "fd_conv2d_igemm: bf16 output needs cout == npad in {128,256}");
   if (make_nhwc_map(&p.out_map, out, B, H, W, cout, 0, cout, bh, bw)) return 1;
-  if (npad == 256) return launch_conv<256, false>(p, max_ctas, stream);
-  return launch_conv<128, false>(p, max_ctas, stream);
+  if (npad == 256) return pair ? launch_conv<256, false, true>(p, max_ctas, stream)
+                               : launch_conv<256, false, false>(p, max_ctas, stream);
+  return pair ? launch_conv<128, false, true>(p, max_ctas, stream)
+              : launch_conv<128, false, false>(p, max_ctas, stream);
 }

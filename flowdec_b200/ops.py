@@ -9,6 +9,9 @@ import torch
 
 from . import _lib
 
+# CTA-pair (cta_group::2) convolution tiles; tests flip this to compare both MMA variants
+CTA_PAIRS = True
+
 # when set to a list, conv_igemm appends (start_event, end_event, algorithmic_flops) per launch
 # (bench.py's roofline leg; events are recorded on the launching stream)
 PROFILE = None
@@ -58,7 +61,7 @@ def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None):
         e0.record()
     rc = L.fd_conv2d_igemm(arr, n, _lib.ptr(wpacked), ktot, _lib.ptr(bias), _lib.ptr(out),
                            int(out_f32), out.shape[3], npad, B, H, W, _lib.ptr(stats), max_ctas,
-                           _lib.stream_ptr())
+                           int(CTA_PAIRS), _lib.stream_ptr())
     _lib.check(rc, "fd_conv2d_igemm")
     if PROFILE is not None:
         e1.record()

@@ -49,10 +49,11 @@ struct fd_conv_src {
  * stats (bf16 output only, may be NULL): GroupNorm partial sums of the OUTPUT, fp32
  * [B, S, cout, 2] with S = 4 * H*W/128 slabs (one per epilogue warp and tile), consumed by
  * fd_gn_finalize — the statistics pass of the next GroupNorm fused into this conv's epilogue.
- * max_ctas: 0 = one persistent CTA per SM. */
+ * max_ctas: 0 = one persistent CTA per SM.  cta_pairs != 0: CTA pairs (cta_group::2, 256-row MMAs,
+ * weight tile split across the pair) when the tile count is even; 0 = single-CTA MMAs. */
 int fd_conv2d_igemm(const struct fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot,
                     const float* bias, void* out, int out_is_f32, int cout, int npad, int B, int H,
-                    int W, float* stats, int max_ctas, fd_stream_t stream);
+                    int W, float* stats, int max_ctas, int cta_pairs, fd_stream_t stream);
 
 /* ---- GroupNorm + SiLU + FIR resampling ------------------------------------------------------
  * replace nn.GroupNorm / nn.SiLU (layerspp.py:229,241,253,274; ncsnpp.py:216,228) and

@@ -14,6 +14,16 @@ from flowdec_b200.ops import conv_igemm, pack_conv_weight
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[True, False], ids=["cta_pair", "single_cta"])
+def _mma_variant(request):
+    """every conv test runs with cta_group::2 pairs and with single-CTA MMAs"""
+    from flowdec_b200 import ops
+    old = ops.CTA_PAIRS
+    ops.CTA_PAIRS = request.param
+    yield
+    ops.CTA_PAIRS = old
+
+
 def _ref_conv(x_nhwc_bf16, w_oihw_bf16, bias):
     x = x_nhwc_bf16.float().permute(0, 3, 1, 2)
     y = F.conv2d(x, w_oihw_bf16.float(), bias, padding=w_oihw_bf16.shape[-1] // 2)
@@ -80,6 +90,29 @@ def test_conv_f32_out_4ch():
     ref = _ref_conv(x, w, b)
     err = (out - ref).abs().max().item()
     assert err <= 1e-4 * ref.abs().max().item() + 1e-4, err
+
+
+def test_conv_epilogue_stats():
+    """GroupNorm partial sums written by the conv epilogue == column sums of the output"""
+    from flowdec_b200 import ops
+    torch.manual_seed(4)
+    dev = "cuda"
+    B, H, W, C = 2, 32, 64, 256
+    x = torch.randn(B, H, W, 128, device=dev).to(torch.bfloat16)
+    w = (torch.randn(C, 128, 3, 3, device=dev) / 34).to(torch.bfloat16)
+    b = torch.randn(C, device=dev)
+    wp = pack_conv_weight([(w, 9)], npad=C)
+    out = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
+    S = ops.conv_stats_slabs(H, W)
+    st = torch.full((B, S, C, 2), float("nan"), device=dev)
+    conv_igemm([(x, 0, 128, 9)], wp, b, out, stats=st)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, b).double()
+    tot = st.double().sum(1)
+    assert torch.allclose(tot[..., 0], ref.sum((1, 2)), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(tot[..., 1], (ref * ref).sum((1, 2)), rtol=1e-5, atol=1e-2)
+    red = ops.slab_reduce(st, 16, torch.empty(B, 16, C, 2, device=dev))
+    assert torch.allclose(red.double().sum(1), tot, rtol=1e-6, atol=1e-3)
 
 
 def test_conv_many_tiles_persistent():
