@@ -1,0 +1,158 @@
+"""Upstream NDAC (DAC) decode path on B200.
+
+API mirror of the part of descript-audio-codec 1.0.0 the reference's demo uses
+(/root/reference/demo.ipynb:56,101-105):
+
+    dac_model = DAC.load(".../weights.pth"); dac_model.to("cuda"); dac_model.eval()
+    zq, _, _ = dac_model.quantizer.from_codes(codes)
+    xhat_ndac = dac_model.decode(zq)
+
+`weights.pth` is audiotools' `{"state_dict": ..., "metadata": {"kwargs": {...}}}`; every
+hyper-parameter (decoder_dim, decoder_rates, n_codebooks, codebook_size, codebook_dim,
+latent_dim / encoder_dim + encoder_rates, sample_rate) comes from that metadata.  Weight-norm
+(`weight_g`, `weight_v`) is folded once at load.  The encoder (`preprocess`/`encode`) is the next
+row to build and raises NotImplementedError.
+
+All arithmetic of from_codes/decode runs in csrc/fd_dac.cu; there is no fallback.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _fold_weight_norm(sd, p):
+    v, g = sd[p + ".weight_v"].float(), sd[p + ".weight_g"].float()
+    return (g * v / v.norm(dim=tuple(range(1, v.ndim)), keepdim=True)).contiguous()
+
+
+class _Quantizer:
+    def __init__(self, owner):
+        self._o = owner
+
+    def from_codes(self, codes):
+        """codes int64 [B, n_q, T] -> (z_q [B, D, T], None, codes); reference call site demo.ipynb:104."""
+        o = self._o
+        o._require_cuda()
+        codes = codes.to(o.device, torch.int64).contiguous()
+        B, nq, T = codes.shape
+        if nq > o.n_codebooks:
+            raise ValueError(f"codes use {nq} codebooks, model has {o.n_codebooks}")
+        z = torch.empty(B, o.latent_dim, T, device=o.device, dtype=torch.float32)
+        rc = _lib.lib().fd_rvq_from_codes(_lib.ptr(codes), _lib.ptr(o.codebooks), _lib.ptr(o.out_proj_w),
+                                          _lib.ptr(o.out_proj_b), _lib.ptr(z), B, nq, T, o.latent_dim,
+                                          o.codebook_dim, o.codebook_size, _lib.stream_ptr())
+        _lib.check(rc, "fd_rvq_from_codes")
+        return z, None, codes
+
+
+class DAC(nn.Module):
+    """decode half of dac.DAC (dac/model/dac.py) running on hand-written CUDA kernels"""
+
+    def __init__(self, state_dict, decoder_dim=1536, decoder_rates=(8, 8, 4, 2), n_codebooks=9,
+                 codebook_size=1024, codebook_dim=8, latent_dim=None, encoder_dim=64,
+                 encoder_rates=(2, 4, 8, 8), sample_rate=44100, **unused):
+        super().__init__()
+        self.decoder_dim, self.decoder_rates = int(decoder_dim), [int(r) for r in decoder_rates]
+        self.n_codebooks, self.codebook_size, self.codebook_dim = int(n_codebooks), int(codebook_size), int(codebook_dim)
+        self.latent_dim = int(latent_dim) if latent_dim is not None else int(encoder_dim * 2 ** len(encoder_rates))
+        self.sample_rate = int(sample_rate)
+        self.hop_length = int(np.prod(self.decoder_rates))
+        sd = state_dict
+        # --- RVQ tables
+        self.register_buffer("codebooks", torch.stack(
+            [sd[f"quantizer.quantizers.{i}.codebook.weight"].float() for i in range(self.n_codebooks)]).contiguous())
+        self.register_buffer("out_proj_w", torch.stack(
+            [_fold_weight_norm(sd, f"quantizer.quantizers.{i}.out_proj").squeeze(-1) for i in range(self.n_codebooks)]).contiguous())
+        self.register_buffer("out_proj_b", torch.stack(
+            [sd[f"quantizer.quantizers.{i}.out_proj.bias"].float() for i in range(self.n_codebooks)]).contiguous())
+        # --- decoder layers as a flat op list
+        self._ops = []
+        m = "decoder.model."
+
+        def reg(name, t):
+            self.register_buffer(name.replace(".", "_"), t.float().contiguous())
+            return getattr(self, name.replace(".", "_"))
+
+        def conv(p):
+            return reg(p + ".w", _fold_weight_norm(sd, p)), reg(p + ".b", sd[p + ".bias"])
+
+        w, b = conv(m + "0")
+        self._ops.append(("conv", w, b, None, 1, 3, False, False))
+        for i, s in enumerate(self.decoder_rates):
+            blk = f"{m}{i + 1}.block."
+            a = reg(blk + "0.alpha", sd[blk + "0.alpha"].reshape(-1))
+            w, b = conv(blk + "1")
+            self._ops.append(("convtr", w, b, a, s, math.ceil(s / 2)))
+            for j, d in enumerate((1, 3, 9)):
+                r = f"{blk}{j + 2}.block."
+                a1 = reg(r + "0.alpha", sd[r + "0.alpha"].reshape(-1))
+                w1, b1 = conv(r + "1")
+                a2 = reg(r + "2.alpha", sd[r + "2.alpha"].reshape(-1))
+                w2, b2 = conv(r + "3")
+                self._ops.append(("res", (w1, b1, a1, d), (w2, b2, a2)))
+        n = len(self.decoder_rates)
+        a = reg(f"{m}{n + 1}.alpha", sd[f"{m}{n + 1}.alpha"].reshape(-1))
+        w, b = conv(f"{m}{n + 2}")
+        self._ops.append(("conv", w, b, a, 1, 3, False, True))
+        self.quantizer = _Quantizer(self)
+
+    @property
+    def device(self):
+        return self.codebooks.device
+
+    def _require_cuda(self):
+        if self.device.type != "cuda":
+            raise RuntimeError("flowdec_b200.ndac runs on CUDA (sm_100a) only; call .to('cuda')")
+
+    @classmethod
+    def load(cls, location, *args, **kwargs):
+        """audiotools.ml.BaseModel.load for package-less checkpoints: {"state_dict", "metadata": {"kwargs"}}"""
+        ckpt = torch.load(str(location), map_location="cpu", weights_only=False)
+        kw = dict(ckpt["metadata"]["kwargs"])
+        kw.update(kwargs)
+        return cls(ckpt["state_dict"], **kw)
+
+    # ---------------------------------------------------------------------------------------
+    def _conv(self, x, w, b, alpha, dil, pad, res=None, tanh=False):
+        B, Cin, Tin = x.shape
+        Cout, _, K = w.shape
+        Tout = Tin + 2 * pad - dil * (K - 1)
+        out = torch.empty(B, Cout, Tout, device=x.device, dtype=torch.float32)
+        rc = _lib.lib().fd_dac_conv1d(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(alpha), _lib.ptr(res),
+                                      _lib.ptr(out), B, Cin, Cout, Tin, K, dil, pad, int(tanh), _lib.stream_ptr())
+        _lib.check(rc, "fd_dac_conv1d")
+        return out
+
+    @torch.no_grad()
+    def decode(self, z):
+        """z [B, latent_dim, T] -> waveform [B, 1, ~T*hop] (dac.DAC.decode, demo.ipynb:105)"""
+        self._require_cuda()
+        x = z.to(self.device, torch.float32).contiguous()
+        for op in self._ops:
+            if op[0] == "conv":
+                _, w, b, a, dil, pad, _, tanh = op
+                x = self._conv(x, w, b, a, dil, pad, tanh=tanh)
+            elif op[0] == "convtr":
+                _, w, b, a, s, pad = op
+                B, Cin, Tin = x.shape
+                Cout = w.shape[1]
+                Tout = (Tin - 1) * s - 2 * pad + 2 * s
+                out = torch.empty(B, Cout, Tout, device=x.device, dtype=torch.float32)
+                rc = _lib.lib().fd_dac_conv_transpose1d(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(a),
+                                                        _lib.ptr(out), B, Cin, Cout, Tin, s, pad, _lib.stream_ptr())
+                _lib.check(rc, "fd_dac_conv_transpose1d")
+                x = out
+            else:
+                _, (w1, b1, a1, d), (w2, b2, a2) = op
+                y = self._conv(x, w1, b1, a1, d, 3 * d)
+                x = self._conv(y, w2, b2, a2, 1, 0, res=x)
+        return x
+
+    def preprocess(self, *a, **k):
+        raise NotImplementedError("NDAC encoder side (preprocess/encode) is the next row to build (SURVEY.md §8f-1)")
+
+    encode = preprocess

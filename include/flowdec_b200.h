@@ -116,6 +116,23 @@ int fd_stft1534_compress(const float* y, int B, int L, const float* normfac, con
 int fd_istft1534_decompress(const void* X, int B, int Tp, int L, const float* window, const void* tw,
                             const float* normfac, float alpha, float beta, float* out, fd_stream_t stream);
 
+/* ---- upstream NDAC (descript-audio-codec 1.0.0; call sites demo.ipynb:101-105) ----------------
+ * layout [B, C, T] fp32 as upstream; weight-norm already folded into w. */
+/* dac.nn.quantize.ResidualVectorQuantize.from_codes: z[b,d,t] = sum_i out_proj_i(codebook_i[codes[b,i,t]])
+ * codes int64 [B,nq,T]; codebooks [nq_total,csize,cdim]; out_proj_w [nq_total,D,cdim]; out_proj_b [nq_total,D] */
+int fd_rvq_from_codes(const long long* codes, const float* codebooks, const float* out_proj_w,
+                      const float* out_proj_b, float* z, int B, int nq, int T, int D, int codebook_dim,
+                      int codebook_size, fd_stream_t stream);
+/* WNConv1d with optional Snake1d on the input (alpha [Cin] or NULL), optional residual add and tanh:
+ * out[b,co,t] = epi(bias[co] + sum w[co,ci,k] * snake(x[b,ci,t + k*dilation - pad])) (+ residual) */
+int fd_dac_conv1d(const float* x, const float* w, const float* bias, const float* snake_alpha,
+                  const float* residual, float* out, int B, int Cin, int Cout, int Tin, int K, int dilation,
+                  int pad, int do_tanh, fd_stream_t stream);
+/* Snake1d -> WNConvTranspose1d(kernel 2*stride, stride, padding pad); w [Cin,Cout,2*stride] */
+int fd_dac_conv_transpose1d(const float* x, const float* w, const float* bias, const float* snake_alpha,
+                            float* out, int B, int Cin, int Cout, int Tin, int stride, int pad,
+                            fd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,108 @@
+"""TEST INFRASTRUCTURE — CPU oracle for the upstream NDAC (DAC) decode path.
+
+The codec is NOT in the reference tree: it is the un-vendored dependency
+`descript-audio-codec==1.0.0` (requirements.txt:4; call sites demo.ipynb:56,101-105:
+`dac.quantizer.from_codes(codes)` -> `dac.decode(zq)`).  This file restates its published
+algorithm (dac/model/dac.py `Decoder`, `DecoderBlock`, `ResidualUnit`; dac/nn/layers.py
+`Snake1d`, `WNConv1d`, `WNConvTranspose1d`; dac/nn/quantize.py `ResidualVectorQuantize.from_codes`)
+on a descript-style state_dict (weight-normalised convs stored as weight_g / weight_v).
+
+Pinning: descript-audio-codec itself is not installed, so this oracle is pinned against the
+architecturally identical port in `transformers.models.dac` (tests/test_dac_cpu.py maps the
+weights and compares); vs descript's own code it is "parity unpinned" (no copy available offline).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def wn(sd, p):
+    """torch.nn.utils.weight_norm (dim=0): w = g * v / ||v||, norm over all dims but the first."""
+    v, g = sd[p + ".weight_v"], sd[p + ".weight_g"]
+    return g * v / v.norm(dim=tuple(range(1, v.ndim)), keepdim=True)
+
+
+def snake(x, alpha):
+    """dac/nn/layers.py snake(): x + (alpha + 1e-9)^-1 * sin(alpha x)^2, alpha [1,C,1]"""
+    return x + (alpha + 1e-9).reciprocal() * torch.sin(alpha * x).pow(2)
+
+
+def from_codes(sd, codes, prefix="quantizer."):
+    """ResidualVectorQuantize.from_codes: z_q = sum_i out_proj_i(codebook_i[codes[:, i]]^T).
+    codes int64 [B, n_q, T] -> z_q [B, D, T]"""
+    z = 0.0
+    for i in range(codes.shape[1]):
+        q = f"{prefix}quantizers.{i}."
+        e = F.embedding(codes[:, i, :], sd[q + "codebook.weight"]).transpose(1, 2)      # [B, 8, T]
+        z = z + F.conv1d(e, wn(sd, q + "out_proj"), sd[q + "out_proj.bias"])
+    return z
+
+
+def residual_unit(sd, p, x, dilation):
+    """ResidualUnit: Snake -> WNConv1d(k7, dilation, pad 3*dilation) -> Snake -> WNConv1d(k1); + x"""
+    y = snake(x, sd[p + ".block.0.alpha"])
+    y = F.conv1d(y, wn(sd, p + ".block.1"), sd[p + ".block.1.bias"], dilation=dilation, padding=3 * dilation)
+    y = snake(y, sd[p + ".block.2.alpha"])
+    y = F.conv1d(y, wn(sd, p + ".block.3"), sd[p + ".block.3.bias"])
+    return x + y
+
+
+def decode(sd, z, rates, prefix="decoder."):
+    """Decoder: WNConv1d(k7) -> [Snake -> WNConvTranspose1d(k=2s, stride s, pad ceil(s/2)) ->
+    ResidualUnit x3 (dilation 1, 3, 9)] per rate -> Snake -> WNConv1d(k7 -> 1) -> tanh"""
+    m = prefix + "model."
+    x = F.conv1d(z, wn(sd, m + "0"), sd[m + "0.bias"], padding=3)
+    for i, s in enumerate(rates):
+        b = f"{m}{i + 1}.block."
+        x = snake(x, sd[b + "0.alpha"])
+        x = F.conv_transpose1d(x, wn(sd, b + "1"), sd[b + "1.bias"], stride=s, padding=math.ceil(s / 2))
+        for j, d in enumerate((1, 3, 9)):
+            x = residual_unit(sd, f"{b}{j + 2}", x, d)
+    n = len(rates)
+    x = snake(x, sd[f"{m}{n + 1}.alpha"])
+    x = F.conv1d(x, wn(sd, f"{m}{n + 2}"), sd[f"{m}{n + 2}.bias"], padding=3)
+    return torch.tanh(x)
+
+
+def synth_dac_state_dict(latent_dim, decoder_dim, rates, n_codebooks, codebook_size=1024, codebook_dim=8,
+                         seed=0):
+    """descript-style decoder + quantizer state_dict with seeded non-degenerate values"""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(p, cout, cin, k, transpose=False):
+        shape = (cin, cout, k) if transpose else (cout, cin, k)
+        v = torch.randn(shape, generator=g)
+        fan = cin * k if not transpose else cin * k / 2
+        sd[p + ".weight_v"] = v
+        sd[p + ".weight_g"] = (torch.rand(shape[0], 1, 1, generator=g) + 0.5) * (
+            v.norm(dim=(1, 2), keepdim=True) / math.sqrt(fan) * (math.sqrt(cin / cout) if transpose else 1.0))
+        sd[p + ".bias"] = 0.05 * torch.randn(cout, generator=g)
+
+    def alpha(p, c):
+        sd[p] = 0.5 + torch.rand(1, c, 1, generator=g)
+
+    for i in range(n_codebooks):
+        q = f"quantizer.quantizers.{i}."
+        sd[q + "codebook.weight"] = torch.randn(codebook_size, codebook_dim, generator=g)
+        conv(q + "out_proj", latent_dim, codebook_dim, 1)
+        conv(q + "in_proj", codebook_dim, latent_dim, 1)
+    m = "decoder.model."
+    conv(m + "0", decoder_dim, latent_dim, 7)
+    ch = decoder_dim
+    for i, s in enumerate(rates):
+        b = f"{m}{i + 1}.block."
+        alpha(b + "0.alpha", ch)
+        conv(b + "1", ch // 2, ch, 2 * s, transpose=True)
+        ch //= 2
+        for j in range(3):
+            r = f"{b}{j + 2}.block."
+            alpha(r + "0.alpha", ch)
+            conv(r + "1", ch, ch, 7)
+            alpha(r + "2.alpha", ch)
+            conv(r + "3", ch, ch, 1)
+    n = len(rates)
+    alpha(f"{m}{n + 1}.alpha", ch)
+    conv(f"{m}{n + 2}", 1, ch, 7)
+    return sd
