@@ -45,6 +45,7 @@ SIGNATURES = {
     "fd_pack4": [_P, _P, _P, _Z, _P],
     "fd_fir_down4": [_P, _P, _I, _I, _I, _P],
     "fd_pyramid_up_add": [_P, _P, _P, _I, _I, _I, _P],
+    "fd_pyramid_gather": [_P, _I, _P, _P, _P, _I, _I, _I, _P],
     "fd_conv_in": [_P, _P, _P, _P, _I, _I, _I, _P],
     "fd_combine": [_P, _P, _P, _P, _P, _Z, _I, _P],
     "fd_output_axpy": [_P, ctypes.POINTER(ctypes.c_float), _P, _F, _P, _F, _F, _P, _P, _Z, _P],

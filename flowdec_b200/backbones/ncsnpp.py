@@ -180,6 +180,7 @@ class NCSNpp(nn.Module):
         self._ws = _Workspace()
         self.stats_slabs = 64
         self.fuse_stats = True     # GroupNorm partial sums produced by the conv epilogue
+        self.pyramid_shift_after_gemm = True
         self.max_ctas = 0
 
     # ------------------------------------------------------------------ parameter management
@@ -248,7 +249,8 @@ class NCSNpp(nn.Module):
                 elif isinstance(m, nn.Conv2d) and i > 3:     # pyramid conv C -> 4
                     b16 = torch.zeros(16, device=dev)
                     b16[:m.bias.shape[0]] = m.bias.float()
-                    P[i] = dict(w=ops.pack_conv_weight([(m.weight.float(), 9)], 16), b=b16)
+                    P[i] = dict(w=ops.pack_conv_weight([(m.weight.float(), 9)], 16), b=b16,
+                                wt=ops.pack_tap_weight(m.weight.float()), b4=m.bias.float().contiguous())
             P["conv_in_w"] = self.all_modules[3].weight.float().contiguous()
             P["conv_in_b"] = self.all_modules[3].bias.float().contiguous()
             P["Wf"] = self.all_modules[0].W.float().contiguous()
@@ -429,9 +431,17 @@ class NCSNpp(nn.Module):
             idx += 1
             pc = P[idx]
             ph = ws.get(f"pyr_out{lvl}", (B, H, W, 4), torch.float32, dev)
-            ops.conv_igemm([(a, 0, a.shape[3], 9)], pc["w"], pc["b"], ph, self.max_ctas)
+            if self.pyramid_shift_after_gemm:
+                # one pass over `a`: 36 per-tap products per pixel on tensor cores, then a gather-sum
+                part = ws.get("pyr_part", (B, H, W, 36), torch.float32, dev)
+                ops.conv_igemm([(a, 0, a.shape[3], 1)], pc["wt"], None, part, self.max_ctas,
+                               algo_k=9 * a.shape[3], algo_cout=4)
+                ops.pyramid_gather(part, pc["b4"], pyramid, ph)
+                pyramid = ph
+            else:
+                ops.conv_igemm([(a, 0, a.shape[3], 9)], pc["w"], pc["b"], ph, self.max_ctas)
+                pyramid = ph if pyramid is None else ops.pyramid_up_add(pyramid, ph, ph)
             idx += 1
-            pyramid = ph if pyramid is None else ops.pyramid_up_add(pyramid, ph, ph)
             if lvl != 0:
                 h = self._resblock(idx, [h], tb, scache)
                 idx += 1

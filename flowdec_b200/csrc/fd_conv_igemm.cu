@@ -58,6 +58,7 @@ struct ConvCfg {
   static constexpr int kBRows = CTA2 ? N / 2 : N;
   static constexpr int kBBytes = kBRows * kSliceK * 2;
   static constexpr int kStages = (N == 256) ? (CTA2 ? 6 : 4) : (N == 128 ? (CTA2 ? 8 : 6) : 8);
+  static_assert(kBBytes % 1024 == 0, "B stage must keep the 1024-byte swizzle alignment");
   static constexpr int kOutBytes = (N >= 64) ? 2 * kTileM * 128 : 0;  // two 64-channel staging tiles
   static constexpr int kTmemCols = (2 * N <= 32) ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes =
@@ -275,26 +276,31 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                              static_cast<uint32_t>(acc * N);
       if constexpr (OUT_F32) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_row, v);
-        tmem_ld_wait();
-        tc_fence_before_sync();
-        mbar_arrive(&tempty_bar[acc]);   // OUT_F32 is single-CTA only
         const int hl = row / p.bw;
         const int wl = row - hl * p.bw;
         const size_t pix = (static_cast<size_t>(n) * p.H + (h0 + hl)) * p.W + (w0 + wl);
         float* o = p.out_f32 + pix * p.cout_valid;
-        if (p.cout_valid == 4) {
-          float4 r;
-          r.x = __uint_as_float(v[0]) + sBias[0];
-          r.y = __uint_as_float(v[1]) + sBias[1];
-          r.z = __uint_as_float(v[2]) + sBias[2];
-          r.w = __uint_as_float(v[3]) + sBias[3];
-          *reinterpret_cast<float4*>(o) = r;
-        } else {
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < p.cout_valid) o[c] = __uint_as_float(v[c]) + sBias[c];
+        for (int g = 0; g < N / 16; ++g) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_row + g * 16, v);
+          tmem_ld_wait();
+          if (g == N / 16 - 1) {
+            tc_fence_before_sync();
+            mbar_arrive(&tempty_bar[acc]);   // OUT_F32 is single-CTA only
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = g * 16 + q * 4;
+            if (c + 3 < p.cout_valid) {
+              float4 r;
+              r.x = __uint_as_float(v[q * 4 + 0]) + sBias[c + 0];
+              r.y = __uint_as_float(v[q * 4 + 1]) + sBias[c + 1];
+              r.z = __uint_as_float(v[q * 4 + 2]) + sBias[c + 2];
+              r.w = __uint_as_float(v[q * 4 + 3]) + sBias[c + 3];
+              *reinterpret_cast<float4*>(o + c) = r;
+            }
+          }
         }
       } else {
         constexpr int kChunks = N / 64;
@@ -459,7 +465,7 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
                                int B, int H, int W, float* stats, int max_ctas, int cta_pairs, cudaStream_t stream) {
   using namespace fd;
   FD_REQUIRE(nsrc >= 1 && nsrc <= kMaxSeg, "fd_conv2d_igemm: nsrc=%d out of range [1,%d]", nsrc, kMaxSeg);
-  FD_REQUIRE(npad == 16 || npad == 128 || npad == 256, "fd_conv2d_igemm: npad=%d unsupported", npad);
+  FD_REQUIRE(npad == 16 || npad == 48 || npad == 128 || npad == 256, "fd_conv2d_igemm: npad=%d unsupported", npad);
   FD_REQUIRE(W % 8 == 0 && W >= 8, "fd_conv2d_igemm: W=%d must be a multiple of 8", W);
   int bw = 8;
   while (bw < 128 && W % (bw * 2) == 0) bw *= 2;
@@ -499,8 +505,10 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
   p.stats = stats;
   if (out_is_f32) {
     FD_REQUIRE(stats == nullptr, "fd_conv2d_igemm: stats are produced by the bf16-output kernels only");
-    FD_REQUIRE(npad == 16 && cout >= 1 && cout <= 16, "fd_conv2d_igemm: fp32 output needs npad=16");
+    FD_REQUIRE((npad == 16 || npad == 48) && cout >= 4 && cout <= npad && cout % 4 == 0,
+               "fd_conv2d_igemm: fp32 output needs npad in {16,48} and cout %% 4 == 0 (got %d/%d)", npad, cout);
     p.out_f32 = static_cast<float*>(out);
+    if (npad == 48) return launch_conv<48, true, false>(p, max_ctas, stream);
     return launch_conv<16, true, false>(p, max_ctas, stream);
   }
   FD_REQUIRE(cout == npad && npad >= 128, "fd_conv2d_igemm: bf16 output needs cout == npad in {128,256}");

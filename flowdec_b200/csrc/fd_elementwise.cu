@@ -168,47 +168,75 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
 //   MODE 0: unit = 1 pixel;  MODE 1: unit = 2x2 output patch (6x6 inputs, each activated once);
 //   MODE 2: unit = 1 input pixel -> 2x2 output quad (3x3 inputs).
 // ------------------------------------------------------------------------------------------
-struct Oct {
+template <int CPT>
+struct ChanSlice {
   const __nv_bfloat16* img;  // source image base (+ channel offset) of this sample
   int Cs;                    // channel pitch of that source
-  float sc[8], sh[8];
+  float sc[CPT], sh[CPT];
 };
 
-template <bool ACT, bool FAST = true>
-__device__ __forceinline__ void load_act(const Oct& o, int H, int W, int hi, int wi, float (&a)[8],
-                                         float (&r)[8], bool want_raw) {
-  if (hi < 0 || hi >= H || wi < 0 || wi >= W) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = r[i] = 0.f;
-    return;
-  }
-  float v[8];
-  load8(o.img + (static_cast<size_t>(hi) * W + wi) * o.Cs, v);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (want_raw) r[i] = v[i];
-    a[i] = ACT ? (FAST ? silu_fast(fmaf(v[i], o.sc[i], o.sh[i])) : silu_f(fmaf(v[i], o.sc[i], o.sh[i]))) : v[i];
+template <int CPT>
+__device__ __forceinline__ void loadN(const __nv_bfloat16* p, float (&v)[CPT]) {
+  if constexpr (CPT == 8) {
+    load8(p, v);
+  } else {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
   }
 }
 
+template <int CPT>
+__device__ __forceinline__ void storeN(__nv_bfloat16* p, const float (&v)[CPT]) {
+  if constexpr (CPT == 8) {
+    store8(p, v);
+  } else {
+    uint2 r;
+    r.x = pack_bf16x2(v[0], v[1]);
+    r.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+}
+
+template <bool ACT, int CPT>
+__device__ __forceinline__ void load_act(const ChanSlice<CPT>& o, int H, int W, int hi, int wi,
+                                         float (&a)[CPT], float (&r)[CPT], bool want_raw) {
+  if (hi < 0 || hi >= H || wi < 0 || wi >= W) {
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) a[i] = r[i] = 0.f;
+    return;
+  }
+  float v[CPT];
+  loadN<CPT>(o.img + (static_cast<size_t>(hi) * W + wi) * o.Cs, v);
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    if (want_raw) r[i] = v[i];
+    a[i] = ACT ? silu_fast(fmaf(v[i], o.sc[i], o.sh[i])) : v[i];
+  }
+}
+
+// FIR-resampling variants.  A thread owns CPT = 4 channels (keeps the register footprint low
+// enough for >= 3 blocks per SM) of one unit:
+//   MODE 1: unit = 2x2 output patch (6x6 inputs, each activated once);
+//   MODE 2: unit = 1 input pixel -> 2x2 output quad (3x3 inputs).
 template <int MODE, bool ACT, bool RAW>
 __global__ void __launch_bounds__(256) gn_act_resample_kernel(
     const __nv_bfloat16* __restrict__ src1, int C1, const __nv_bfloat16* __restrict__ src2, int C2,
     const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ out,
     __nv_bfloat16* __restrict__ out_raw, int H, int W) {
+  constexpr int CPT = 4;
   const int C = C1 + C2;
-  const int oct = C >> 3;
+  const int slices = C / CPT;
   // units along W at input resolution (MODE 1: pairs of output columns)
   const int UW = (MODE == 1) ? W / 4 : W;
   const int UH = (MODE == 1) ? H / 4 : H;
   const int row_unit = blockIdx.y % UH;
   const int b = blockIdx.y / UH;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= UW * oct) return;
-  const int uw = t / oct;
-  const int o8 = t - uw * oct;
-  const int c0 = o8 * 8;
-  Oct o;
+  if (t >= UW * slices) return;
+  const int uw = t / slices;
+  const int c0 = (t - uw * slices) * CPT;
+  ChanSlice<CPT> o;
   {
     const bool first = c0 < C1;
     o.Cs = first ? C1 : C2;
@@ -216,43 +244,41 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
     if (ACT) {
       const float4* ss = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(b) * C + c0) * 2);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < CPT / 2; ++i) {
         const float4 q = ss[i];
         o.sc[2 * i] = q.x; o.sh[2 * i] = q.y; o.sc[2 * i + 1] = q.z; o.sh[2 * i + 1] = q.w;
       }
     }
   }
-  if (MODE == 0) {
-    // handled by gn_act_kernel (several pixels per thread, scale/shift held in registers)
-  } else if (MODE == 1) {
+  if (MODE == 1) {
     // outputs (2*row_unit + {0,1}, 2*uw + {0,1}); inputs rows 4*row_unit-1 .. +4, cols 4*uw-1 .. +4
     const int Ho = H / 2, Wo = W / 2;
-    float acc[2][2][8], racc[2][2][8];
+    float acc[2][2][CPT], racc[2][2][CPT];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[i][j][c] = racc[i][j][c] = 0.f;
+        for (int c = 0; c < CPT; ++c) acc[i][j][c] = racc[i][j][c] = 0.f;
     const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
 #pragma unroll
     for (int ri = 0; ri < 6; ++ri) {
       const int hi = 4 * row_unit - 1 + ri;
-      float h0[8], h1[8], rh0[8], rh1[8];  // horizontal FIR of this input row for the two output columns
+      float h0[CPT], h1[CPT], rh0[CPT], rh1[CPT];  // horizontal FIR of this input row, two output columns
 #pragma unroll
-      for (int c = 0; c < 8; ++c) h0[c] = h1[c] = rh0[c] = rh1[c] = 0.f;
+      for (int c = 0; c < CPT; ++c) h0[c] = h1[c] = rh0[c] = rh1[c] = 0.f;
 #pragma unroll
       for (int ci = 0; ci < 6; ++ci) {
-        float a[8], r[8];
-        load_act<ACT>(o, H, W, hi, 4 * uw - 1 + ci, a, r, RAW);
+        float a[CPT], r[CPT];
+        load_act<ACT, CPT>(o, H, W, hi, 4 * uw - 1 + ci, a, r, RAW);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           if (ci < 4) { h0[c] = fmaf(k[ci], a[c], h0[c]); if (RAW) rh0[c] = fmaf(k[ci], r[c], rh0[c]); }
           if (ci >= 2) { h1[c] = fmaf(k[ci - 2], a[c], h1[c]); if (RAW) rh1[c] = fmaf(k[ci - 2], r[c], rh1[c]); }
         }
       }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         if (ri < 4) {
           acc[0][0][c] = fmaf(k[ri], h0[c], acc[0][0][c]);
           acc[0][1][c] = fmaf(k[ri], h1[c], acc[0][1][c]);
@@ -270,21 +296,21 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const size_t off = ((static_cast<size_t>(b) * Ho + 2 * row_unit + i) * Wo + 2 * uw + j) * C + c0;
-        store8(out + off, acc[i][j]);
-        if (RAW) store8(out_raw + off, racc[i][j]);
+        storeN<CPT>(out + off, acc[i][j]);
+        if (RAW) storeN<CPT>(out_raw + off, racc[i][j]);
       }
   } else {
     // input pixel (row_unit, uw) -> outputs (2*row_unit + {0,1}, 2*uw + {0,1})
     const int Ho = H * 2, Wo = W * 2;
-    float top[3][8], bot[3][8], rtop[3][8], rbot[3][8];
+    float top[3][CPT], bot[3][CPT], rtop[3][CPT], rbot[3][CPT];
 #pragma unroll
     for (int cj = 0; cj < 3; ++cj) {
-      float a0[8], a1[8], a2[8], r0[8], r1[8], r2[8];
-      load_act<ACT>(o, H, W, row_unit - 1, uw - 1 + cj, a0, r0, RAW);
-      load_act<ACT>(o, H, W, row_unit, uw - 1 + cj, a1, r1, RAW);
-      load_act<ACT>(o, H, W, row_unit + 1, uw - 1 + cj, a2, r2, RAW);
+      float a0[CPT], a1[CPT], a2[CPT], r0[CPT], r1[CPT], r2[CPT];
+      load_act<ACT, CPT>(o, H, W, row_unit - 1, uw - 1 + cj, a0, r0, RAW);
+      load_act<ACT, CPT>(o, H, W, row_unit, uw - 1 + cj, a1, r1, RAW);
+      load_act<ACT, CPT>(o, H, W, row_unit + 1, uw - 1 + cj, a2, r2, RAW);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         top[cj][c] = 0.25f * a0[c] + 0.75f * a1[c];
         bot[cj][c] = 0.75f * a1[c] + 0.25f * a2[c];
         if (RAW) {
@@ -295,9 +321,9 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      float e[8], f[8], re[8], rf[8];
+      float e[CPT], f[CPT], re[CPT], rf[CPT];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         const float* l = i ? bot[0] : top[0];
         const float* m = i ? bot[1] : top[1];
         const float* r = i ? bot[2] : top[2];
@@ -312,11 +338,11 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
         }
       }
       const size_t off = ((static_cast<size_t>(b) * Ho + 2 * row_unit + i) * Wo + 2 * uw) * C + c0;
-      store8(out + off, e);
-      store8(out + off + C, f);
+      storeN<CPT>(out + off, e);
+      storeN<CPT>(out + off + C, f);
       if (RAW) {
-        store8(out_raw + off, re);
-        store8(out_raw + off + C, rf);
+        storeN<CPT>(out_raw + off, re);
+        storeN<CPT>(out_raw + off + C, rf);
       }
     }
   }
@@ -438,6 +464,51 @@ __global__ void pyramid_up_add_kernel(const float4* __restrict__ lo, const float
     tap(hi, wn, 0.1875f);
     tap(hn, wi, 0.1875f);
     tap(hn, wn, 0.0625f);
+    out[idx] = acc;
+  }
+}
+
+// 3x3 conv to 4 channels evaluated as "GEMM first, shift after": the tensor-core kernel produces
+// per-pixel partial products part[b,h,w,tap*4+co] = W_tap[co,:] . a[b,h,w,:] (one pass over a),
+// this kernel sums the 9 shifted partials (+ bias, + FIR-upsampled coarser pyramid):
+//   out[p,co] = bias[co] + sum_tap part[p + delta_tap][tap*4+co] (+ FIR_up(lo)[p,co])
+__global__ void pyramid_gather_kernel(const float* __restrict__ part, int pc, const float* __restrict__ bias,
+                                      const float4* __restrict__ lo, float4* __restrict__ out, int B, int H,
+                                      int W) {
+  const size_t total = static_cast<size_t>(B) * H * W;
+  const float4 bv = make_float4(bias[0], bias[1], bias[2], bias[3]);
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(idx % W);
+    const int h = static_cast<int>((idx / W) % H);
+    const int b = static_cast<int>(idx / (static_cast<size_t>(W) * H));
+    float4 acc = bv;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      const float4 v = *reinterpret_cast<const float4*>(
+          part + ((static_cast<size_t>(b) * H + hh) * W + ww) * pc + t * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (lo != nullptr) {
+      const int Hl = H / 2, Wl = W / 2;
+      const int hi = h >> 1, wi = w >> 1;
+      const int hn = (h & 1) ? hi + 1 : hi - 1;
+      const int wn = (w & 1) ? wi + 1 : wi - 1;
+      auto tap = [&](int y, int x, float wgt) {
+        if (y < 0 || y >= Hl || x < 0 || x >= Wl) return;
+        const float4 v = lo[(static_cast<size_t>(b) * Hl + y) * Wl + x];
+        acc.x = fmaf(wgt, v.x, acc.x);
+        acc.y = fmaf(wgt, v.y, acc.y);
+        acc.z = fmaf(wgt, v.z, acc.z);
+        acc.w = fmaf(wgt, v.w, acc.w);
+      };
+      tap(hi, wi, 0.5625f);
+      tap(hi, wn, 0.1875f);
+      tap(hn, wi, 0.1875f);
+      tap(hn, wn, 0.0625f);
+    }
     out[idx] = acc;
   }
 }
@@ -664,11 +735,12 @@ extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, in
   FD_REQUIRE(out == nullptr || scale_shift != nullptr, "fd_gn_act_resample: activated output needs scale_shift");
   FD_REQUIRE(mode != 0 || out != nullptr, "fd_gn_act_resample: mode 0 without activation is a copy");
   const int oct = (C1 + C2) / 8;
+  const int slices = (C1 + C2) / 4;   // FIR variants: 4 channels per thread
   const int UW = mode == 1 ? W / 4 : W;
   const int UH = mode == 1 ? H / 4 : H;
   FD_REQUIRE(static_cast<long long>(B) * UH <= 65535 && oct <= 256,
              "fd_gn_act_resample: B*rows=%lld exceeds grid.y (or C > 2048)", static_cast<long long>(B) * UH);
-  dim3 grid((UW * oct + 255) / 256, B * UH);
+  dim3 grid((UW * slices + 255) / 256, B * UH);
   const bf16* s1 = static_cast<const bf16*>(src1);
   const bf16* s2 = static_cast<const bf16*>(src2);
   bf16* o = static_cast<bf16*>(out);
@@ -715,6 +787,14 @@ extern "C" int fd_pyramid_up_add(const void* lo, const void* add, void* out, int
       static_cast<const float4*>(lo), static_cast<const float4*>(add), static_cast<float4*>(out), B, H,
       W);
   return check_launch("fd_pyramid_up_add");
+}
+
+extern "C" int fd_pyramid_gather(const float* part, int part_channels, const float* bias, const void* lo4,
+                                 void* out4, int B, int H, int W, cudaStream_t stream) {
+  FD_REQUIRE(part_channels >= 36 && part_channels % 4 == 0, "fd_pyramid_gather: part_channels=%d", part_channels);
+  pyramid_gather_kernel<<<grid_for(static_cast<size_t>(B) * H * W, 256), 256, 0, stream>>>(
+      part, part_channels, bias, static_cast<const float4*>(lo4), static_cast<float4*>(out4), B, H, W);
+  return check_launch("fd_pyramid_gather");
 }
 
 extern "C" int fd_conv_in(const void* in4, const float* w, const float* bias, void* out, int B, int H,

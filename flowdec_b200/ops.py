@@ -41,7 +41,7 @@ def conv_stats_slabs(H, W):
     return 4 * (H * W // 128)
 
 
-def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None):
+def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None, algo_cout=None):
     """srcs: list of (tensor NHWC bf16, c_begin, c_count, taps). out: NHWC bf16 [.., npad] or fp32 [.., cout<=16]."""
     L = _lib.lib()
     n = len(srcs)
@@ -70,7 +70,7 @@ def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None):
         k_algo = sum(cc * taps for (_, _, cc, taps) in srcs)
         if algo_k is not None:
             k_algo = algo_k
-        PROFILE.append((e0, e1, 2.0 * B * H * W * out.shape[3] * k_algo))
+        PROFILE.append((e0, e1, 2.0 * B * H * W * (algo_cout or out.shape[3]) * k_algo))
     return out
 
 
@@ -139,6 +139,21 @@ def pyramid_up_add(lo, add, out):
     B, H, W, _ = lo.shape
     _lib.check(_lib.lib().fd_pyramid_up_add(_lib.ptr(lo), _lib.ptr(add), _lib.ptr(out), B, H, W,
                                             _lib.stream_ptr()), "fd_pyramid_up_add")
+    return out
+
+
+def pack_tap_weight(w, npad=48):
+    """[Cout(4), Cin, 3, 3] -> bf16 [npad, Cin]: row tap*4+co = w[co, :, kh, kw] (tap = kh*3+kw)"""
+    cout, cin = w.shape[:2]
+    wp = w.permute(2, 3, 0, 1).reshape(9 * cout, cin).to(torch.bfloat16)
+    pad = torch.zeros(npad - 9 * cout, cin, dtype=wp.dtype, device=wp.device)
+    return torch.cat([wp, pad], 0).contiguous()
+
+
+def pyramid_gather(part, bias4, lo, out):
+    B, H, W, pc = part.shape
+    _lib.check(_lib.lib().fd_pyramid_gather(_lib.ptr(part), pc, _lib.ptr(bias4), _lib.ptr(lo), _lib.ptr(out),
+                                            B, H, W, _lib.stream_ptr()), "fd_pyramid_gather")
     return out
 
 

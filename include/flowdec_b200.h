@@ -44,7 +44,8 @@ struct fd_conv_src {
 /* out[b,h,w,o] = bias[o] + sum_seg sum_tap sum_c src_seg[b,h+dh,w+dw,c] * wpacked[o, k(seg,tap,c)]
  * wpacked: bf16 [npad, ktot], K-major, k ordered segment-major, then tap (kh-major), then channel.
  * out_is_f32 = 0: out bf16 NHWC [B,H,W,cout], cout == npad in {128,256}
- * out_is_f32 = 1: out fp32 NHWC [B,H,W,cout], cout <= 16, npad == 16 (the 4-channel pyramid convs)
+ * out_is_f32 = 1: out fp32 NHWC [B,H,W,cout], cout % 4 == 0, cout <= npad, npad in {16, 48}
+ *                 (the 4-channel pyramid convs, directly or as 36 per-tap partial products)
  * bias: fp32 [npad] or NULL.  Requires W % 8 == 0 and H % (128 / min(128, pow2 divisor of W)) == 0.
  * stats (bf16 output only, may be NULL): GroupNorm partial sums of the OUTPUT, fp32
  * [B, S, cout, 2] with S = 4 * H*W/128 slabs (one per epilogue warp and tile), consumed by
@@ -82,6 +83,11 @@ int fd_pack4(const void* x_f2, const void* y_f2, void* out4, size_t npix, fd_str
 int fd_fir_down4(const void* in4, void* out4, int B, int H, int W, fd_stream_t stream);
 /* ncsnpp.py:355,360: out = FIR_up(lo[B,H,W,4]) + add[B,2H,2W,4] (out may alias add) */
 int fd_pyramid_up_add(const void* lo4, const void* add4, void* out4, int B, int H, int W, fd_stream_t stream);
+/* ncsnpp.py:218,230,355-360 pyramid conv 3x3 C->4 finished "GEMM first, shift after": part fp32
+ * [B,H,W,part_channels] holds the 36 per-tap products W_tap . a (fd_conv2d_igemm, npad 48, 1 tap);
+ * out[p] = bias + sum_tap part[p + delta_tap][tap*4 + co] (+ FIR_up(lo4[B,H/2,W/2,4]) if lo4 != NULL) */
+int fd_pyramid_gather(const float* part, int part_channels, const float* bias, const void* lo4, void* out4,
+                      int B, int H, int W, fd_stream_t stream);
 /* ncsnpp.py:284 input conv 3x3 4->64 (w fp32 OIHW [64,4,3,3]) -> bf16 NHWC [B,H,W,64] */
 int fd_conv_in(const void* in4, const float* w, const float* bias, void* out, int B, int H, int W,
                fd_stream_t stream);

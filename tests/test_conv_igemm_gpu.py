@@ -130,3 +130,27 @@ def test_conv_many_tiles_persistent():
     ref = _ref_conv(x, w, b)
     err = (out.float() - ref).abs().max().item()
     assert err <= 1e-2 * ref.abs().max().item() + 1e-3, err
+
+
+def test_pyramid_conv_gemm_first_shift_after():
+    """3x3 conv to 4 channels as 36 per-tap tensor-core products + gather-sum (+ FIR-up pyramid)"""
+    from flowdec_b200 import ops
+    from oracle import flowdec_oracle as O
+    torch.manual_seed(5)
+    dev = "cuda"
+    B, H, W, Cin = 2, 32, 24, 256
+    x = torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16)
+    w = (torch.randn(4, Cin, 3, 3, device=dev) / 48).to(torch.bfloat16)
+    b = torch.randn(4, device=dev)
+    lo = torch.randn(B, H // 2, W // 2, 4, device=dev)
+    part = torch.empty(B, H, W, 36, device=dev)
+    conv_igemm([(x, 0, Cin, 1)], ops.pack_tap_weight(w.float()), None, part)
+    out = torch.empty(B, H, W, 4, device=dev)
+    ops.pyramid_gather(part, b, None, out)
+    out2 = torch.empty(B, H, W, 4, device=dev)
+    ops.pyramid_gather(part, b, lo, out2)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, b)
+    assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-4
+    ref2 = ref + O.fir_up2(lo.cpu().permute(0, 3, 1, 2)).permute(0, 2, 3, 1).to(dev)
+    assert (out2 - ref2).abs().max().item() <= 1e-4 * ref2.abs().max().item() + 1e-4
