@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--variant", default="75m")
     ap.add_argument("--max-batch", type=int, default=0, help="clips per backbone pass (0 = model default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=0, help="micro-batches in flight (0 = model default)")
     return ap.parse_args()
 
 
@@ -201,7 +202,8 @@ def workload_config(args):
                         f"{args.solver} N={args.N} (NFE {nfe_of(args.N, args.solver)}), Tp={padded_frames(L)} frames",
             "per_gpu_batch": args.batch, "clip_seconds": args.seconds, "nfe": nfe_of(args.N, args.solver),
             "solver": args.solver, "sharding": f"dp{args.gpus} (clip batch, no data-path collective)",
-            "l2": "working set (multi-GB activations per micro-batch) >> 126 MB L2; no explicit flush"}
+            "l2": "working set (multi-GB activations per micro-batch) >> 126 MB L2; no explicit flush",
+            "micro_batch": "clips per backbone pass and concurrent CUDA streams: see model.max_batch / overlap_streams"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -237,6 +239,8 @@ def main():
     model = model.to(dev)
     if args.max_batch:
         model.max_batch = args.max_batch
+    if args.streams:
+        model.overlap_streams = args.streams
     L = int(args.seconds * SR)
     B = args.batch
     nfe = nfe_of(args.N, args.solver)
@@ -307,12 +311,14 @@ def main():
     roofline = None
     if rank == 0:
         model.use_cuda_graph = False
+        lanes_saved, model.overlap_streams = model.overlap_streams, 1   # time the kernel alone on the SMs
         ops.PROFILE = []
         torch.cuda.synchronize()
         model.enhance(y_dev, N=args.N, solver=args.solver)
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         model.use_cuda_graph = True
+        model.overlap_streams = lanes_saved
         conv_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
         conv_flops = sum(f for _, _, f in prof)
         peak, how = load_peaks()

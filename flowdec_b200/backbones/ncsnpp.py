@@ -177,7 +177,8 @@ class NCSNpp(nn.Module):
 
         self._prepared = None      # packed weights (built lazily, dropped on load_state_dict / .to())
         self._temb_cache = {}
-        self._ws = _Workspace()
+        self._workspaces = {}      # lane -> _Workspace (one per concurrently running micro-batch stream)
+        self._lane = 0
         self.stats_slabs = 64
         self.fuse_stats = True     # GroupNorm partial sums produced by the conv epilogue
         self.pyramid_shift_after_gemm = True
@@ -199,8 +200,15 @@ class NCSNpp(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._invalidate()
-        self._ws = _Workspace()
+        self._workspaces = {}
         return super()._apply(fn, *a, **k)
+
+    @property
+    def _ws(self):
+        w = self._workspaces.get(self._lane)
+        if w is None:
+            w = self._workspaces[self._lane] = _Workspace()
+        return w
 
     @staticmethod
     def _npad(cout):
@@ -383,11 +391,13 @@ class NCSNpp(nn.Module):
         return ops.slab_reduce(st, self.stats_slabs, out)
 
     # ------------------------------------------------------------------ forward
-    def velocity(self, x, y, t, out=None, base1=None, c1=0.0, base2=None, c2=0.0, coef=1.0, v_out=None):
+    def velocity(self, x, y, t, out=None, base1=None, c1=0.0, base2=None, c2=0.0, coef=1.0, v_out=None,
+                 lane=0):
         """v = backbone(x, y, t) with the ODE stage fused into the last kernel:
         out = c1*base1 + c2*base2 + coef*v.  x, y, bases, out: fp32 [B,F,T,2] (= complex64 [B,F,T])."""
         P = self.prepare()
         tb = self.temb_biases(t)
+        self._lane = lane            # selects the workspace: lanes may run concurrently on different streams
         ws, dev = self._ws, x.device
         B, Fq, T = x.shape[0], x.shape[1], x.shape[2]
         nres = self.num_resolutions

@@ -71,6 +71,8 @@ class FlowModel(EnhancementModel):
         self._graphs = {}
         self.use_cuda_graph = True
         self.max_batch = 8          # clips per backbone pass (micro-batch)
+        self.overlap_streams = 2    # micro-batches in flight on separate CUDA streams
+        self._streams = []
         self._sig_cache = None
 
     def _apply(self, fn, *a, **k):
@@ -88,6 +90,11 @@ class FlowModel(EnhancementModel):
         if torch.is_tensor(t) and t.ndim == 0:
             t = t.unsqueeze(0)
         return self.backbone(xt, y, t)
+
+    def _side_streams(self, n):
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(device=self.device))
+        return self._streams[:n]
 
     def _sigma_vec(self, Fq):
         if self._sig_cache is None:
@@ -113,14 +120,29 @@ class FlowModel(EnhancementModel):
         ops.x0_noise(st["Y"], self._sigma_vec(768), st["eps"], sigma_fac, st["x"][0])
         cur = 0
         traj = [st["x"][0]] if want_traj else None
+        # weights / time-embedding biases are produced on this stream before any lane forks
+        bb.prepare()
+        for (t, dt) in t_grid(N):
+            for stage in stages(solver, t, dt):
+                bb.temb_biases(float(stage[0]))
         for (t, dt) in t_grid(N):
             bufs = {"x": st["x"][cur], "xn": st["x"][cur ^ 1], "tmp": st["tmp"]}
             for (te, src, dst, b1, c1, b2, c2, coef) in stages(solver, t, dt):
-                for lo in range(0, B, self.max_batch):
-                    hi = min(B, lo + self.max_batch)
+                # micro-batches are independent: alternate them over `overlap_streams` CUDA streams so
+                # the HBM-bound GroupNorm/FIR passes of one overlap the tensor-bound convs of another
+                chunks = [(lo, min(B, lo + self.max_batch)) for lo in range(0, B, self.max_batch)]
+                nlanes = max(1, min(self.overlap_streams, len(chunks)))
+                main = torch.cuda.current_stream()
+                lanes = [main] + self._side_streams(nlanes - 1)
+                for s_ in lanes[1:]:
+                    s_.wait_stream(main)
+                for i, (lo, hi) in enumerate(chunks):
                     sl = lambda name: bufs[name][lo:hi] if name is not None else None
-                    bb.velocity(sl(src), st["Y"][lo:hi], float(te), out=sl(dst), base1=sl(b1), c1=c1,
-                                base2=sl(b2), c2=c2, coef=coef)
+                    with torch.cuda.stream(lanes[i % nlanes]):
+                        bb.velocity(sl(src), st["Y"][lo:hi], float(te), out=sl(dst), base1=sl(b1), c1=c1,
+                                    base2=sl(b2), c2=c2, coef=coef, lane=i % nlanes)
+                for s_ in lanes[1:]:
+                    main.wait_stream(s_)
             cur ^= 1
             if want_traj:
                 keep = torch.empty_like(st["x"][cur])
