@@ -57,7 +57,9 @@ struct ConvCfg {
   // B rows held by one CTA: the pair splits the N weight rows between its two shared memories
   static constexpr int kBRows = CTA2 ? N / 2 : N;
   static constexpr int kBBytes = kBRows * kSliceK * 2;
-  static constexpr int kStages = (N == 256) ? (CTA2 ? 6 : 4) : (N == 128 ? (CTA2 ? 8 : 6) : 8);
+  // the ring is one stage short of what 227 KB would hold: the ~30 KB left let zero-smem blocks of
+  // the HBM-bound GroupNorm / FIR kernels (another micro-batch, another stream) co-reside on the SM
+  static constexpr int kStages = (N == 256) ? (CTA2 ? 5 : 3) : (N == 128 ? (CTA2 ? 6 : 5) : 8);
   static_assert(kBBytes % 1024 == 0, "B stage must keep the 1024-byte swizzle alignment");
   static constexpr int kOutBytes = (N >= 64) ? 2 * kTileM * 128 : 0;  // two 64-channel staging tiles
   static constexpr int kTmemCols = (2 * N <= 32) ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
