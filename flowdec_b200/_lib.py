@@ -48,7 +48,7 @@ SIGNATURES = {
     "fd_pyramid_gather": [_P, _I, _P, _P, _P, _I, _I, _I, _P],
     "fd_conv_in": [_P, _P, _P, _P, _I, _I, _I, _P],
     "fd_combine": [_P, _P, _P, _P, _P, _Z, _I, _P],
-    "fd_output_axpy": [_P, ctypes.POINTER(ctypes.c_float), _P, _F, _P, _F, _F, _P, _P, _Z, _P],
+    "fd_output_axpy": [_P, ctypes.POINTER(ctypes.c_float), _P, _F, _P, _F, _P, _F, _F, _P, _P, _Z, _P],
     "fd_x0": [_P, _P, _P, _F, _P, _I, _I, _I, _P],
     "fd_fourier_embed": [_F, _P, _I, _P, _P],
     "fd_matvec": [_P, _I, _I, _P, _P, _P, _F, _P, _I, _P],

@@ -392,9 +392,9 @@ class NCSNpp(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def velocity(self, x, y, t, out=None, base1=None, c1=0.0, base2=None, c2=0.0, coef=1.0, v_out=None,
-                 lane=0):
+                 lane=0, base3=None, c3=0.0):
         """v = backbone(x, y, t) with the ODE stage fused into the last kernel:
-        out = c1*base1 + c2*base2 + coef*v.  x, y, bases, out: fp32 [B,F,T,2] (= complex64 [B,F,T])."""
+        out = c1*base1 + c2*base2 + c3*base3 + coef*v.  x, y, bases, out: fp32 [B,F,T,2] (= complex64 [B,F,T])."""
         P = self.prepare()
         tb = self.temb_biases(t)
         self._lane = lane            # selects the workspace: lanes may run concurrently on different streams
@@ -459,7 +459,7 @@ class NCSNpp(nn.Module):
         assert not hs and idx == len(mods)
         if out is None and v_out is None:
             v_out = torch.empty(B, Fq, T, 2, device=dev, dtype=torch.float32)
-        ops.output_axpy(pyramid, P["w_out8"], base1, c1, base2, c2, coef, out, v_out)
+        ops.output_axpy(pyramid, P["w_out8"], base1, c1, base2, c2, coef, out, v_out, base3=base3, c3=c3)
         return out if out is not None else v_out
 
     def forward(self, x, y, t):

@@ -612,11 +612,14 @@ __global__ void __launch_bounds__(256) combine_kernel(const float4* __restrict__
   }
 }
 
-// v = W_out[2x4] * pyr ; out = c1*base1 + c2*base2 + coef*v   (complex as float2; fused ODE stage)
+// v = W_out[2x4] * pyr ; out = c1*base1 + c2*base2 + c3*base3 + coef*v   (complex as float2).
+// One fused stage of every sampler: Euler / midpoint / Heun (base1 = x, base2 = predictor state),
+// reverse-diffusion predictor (x, y, noise) and annealed-Langevin corrector (x, noise).
 __global__ void output_axpy_kernel(const float4* __restrict__ pyr, float w00, float w01, float w02,
                                    float w03, float w10, float w11, float w12, float w13,
                                    const float2* __restrict__ base1, float c1,
-                                   const float2* __restrict__ base2, float c2, float coef,
+                                   const float2* __restrict__ base2, float c2,
+                                   const float2* __restrict__ base3, float c3, float coef,
                                    float2* __restrict__ out, float2* __restrict__ v_out, size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -635,6 +638,11 @@ __global__ void output_axpy_kernel(const float4* __restrict__ pyr, float w00, fl
         const float2 a = base2[i];
         r.x = fmaf(c2, a.x, r.x);
         r.y = fmaf(c2, a.y, r.y);
+      }
+      if (base3) {
+        const float2 a = base3[i];
+        r.x = fmaf(c3, a.x, r.x);
+        r.y = fmaf(c3, a.y, r.y);
       }
       out[i] = r;
     }
@@ -819,13 +827,14 @@ extern "C" int fd_combine(const void* pyr4, const float* w, const float* bias, c
 }
 
 extern "C" int fd_output_axpy(const void* pyr4, const float* w_out_host8, const void* base1, float c1,
-                              const void* base2, float c2, float coef, void* out, void* v_out,
-                              size_t npix, cudaStream_t stream) {
+                              const void* base2, float c2, const void* base3, float c3, float coef,
+                              void* out, void* v_out, size_t npix, cudaStream_t stream) {
   const float* w = w_out_host8;  // host pointer: 2x4 weights, passed by value into the launch
   output_axpy_kernel<<<grid_for(npix, 256), 256, 0, stream>>>(
       static_cast<const float4*>(pyr4), w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7],
-      static_cast<const float2*>(base1), c1, static_cast<const float2*>(base2), c2, coef,
-      static_cast<float2*>(out), static_cast<float2*>(v_out), npix);
+      static_cast<const float2*>(base1), c1, static_cast<const float2*>(base2), c2,
+      static_cast<const float2*>(base3), c3, coef, static_cast<float2*>(out), static_cast<float2*>(v_out),
+      npix);
   return check_launch("fd_output_axpy");
 }
 

@@ -11,6 +11,7 @@ per (batch, length, N, solver).
 import warnings
 from typing import Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -231,6 +232,123 @@ class FlowModel(EnhancementModel):
             x_hat = x_hat.squeeze(0)
         x_hat = x_hat.to(y_in.device)
         return (x_hat, info) if return_preprocess_info else x_hat
+
+
+class ScoreModel(EnhancementModel):
+    """Score-based baseline (ScoreDec / SGMSE+) around the same backbone; reference model.py:583-688.
+    Inference path: predictor-corrector sampler with the reverse-diffusion predictor and the
+    annealed-Langevin corrector (sampling/__init__.py:32-72, predictors.py:61-71,
+    correctors.py:43-66).  Each update is affine in (x, y, noise, backbone output) and is fused
+    into the backbone's last kernel, so one sampler step = 1 + corrector_steps kernel chains."""
+
+    def __init__(self, sde, t_eps, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.sde = sde
+        self.t_eps = t_eps
+        self.max_batch = 8
+
+    def sde_std(self, t_batch):
+        t = float(t_batch.flatten()[0]) if torch.is_tensor(t_batch) else float(t_batch)
+        return self.sde._std(t)
+
+    def forward(self, xt, y, t_batch):
+        """score = -backbone(xt, y, t) / sigma_t (model.py:613-628); shared scalar t."""
+        std = float(self.sde_std(t_batch))
+        return -self.backbone(xt, y, t_batch) / std
+
+    @torch.no_grad()
+    def enhance(self, y, sampler_type="pc", predictor="reverse_diffusion", corrector="ald", N=30,
+                corrector_steps=1, snr=0.5, return_preprocess_info=False, denoise=True,
+                probability_flow=False, noise=None, **kwargs):
+        """reference model.py:630-657.  `noise`: optional list of complex64 [B,1,768,Tp] tensors standing
+        in for the sampler's draws, in call order: prior, then per step (corrector draws..., predictor draw)."""
+        if sampler_type != "pc" or predictor != "reverse_diffusion" or corrector not in ("ald", "none"):
+            raise NotImplementedError("flowdec_b200.ScoreModel implements the PC sampler with "
+                                      "reverse_diffusion predictor and ald / none corrector")
+        if probability_flow:
+            raise NotImplementedError("probability_flow=True is not implemented")
+        if corrector == "none":
+            corrector_steps = 0
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("flowdec_b200 runs on CUDA (sm_100a) only; call model.cuda()")
+        y_in = y
+        squeeze_dims = 0
+        while y.ndim < 3:
+            y = y.unsqueeze(0)
+            squeeze_dims += 1
+        B, C, L = y.shape
+        fe, bb, sde = self.feature_extractor, self.backbone, self.sde.copy()
+        sde.N = N
+        Tp = padded_frames(1 + L // 384)
+        f32 = dict(device=dev, dtype=torch.float32)
+        y2 = y.reshape(B * C, L).to(dev, torch.float32).contiguous()
+        nf = torch.empty(B * C, **f32)
+        Y = torch.empty(B * C, 768, Tp, 2, **f32)
+        ops.normfac(y2, 1 if self.normalize_mode == "noisy" else 0, nf)
+        fe.stft_compress(y2, nf, Y)
+        draws = iter(noise) if noise is not None else None
+
+        def draw():
+            if draws is not None:
+                z = next(draws).to(dev, torch.complex64).reshape(B * C, 768, Tp)
+            else:
+                z = torch.randn(B * C, 768, Tp, dtype=torch.complex64, device=dev)
+            return torch.view_as_real(z).contiguous()
+
+        def backbone_stage(x, t, out, c1, c2, base3, c3, coef):
+            for lo in range(0, B * C, self.max_batch):
+                hi = min(B * C, lo + self.max_batch)
+                bb.velocity(x[lo:hi], Y[lo:hi], float(t), out=out[lo:hi], base1=x[lo:hi], c1=c1,
+                            base2=Y[lo:hi], c2=c2, base3=base3[lo:hi] if base3 is not None else None,
+                            c3=c3, coef=coef)
+
+        # prior: x_T = y + z * std(T)     (sdes.py:201-206)
+        x = torch.empty_like(Y)
+        xn = torch.empty_like(Y)
+        x_mean = torch.empty_like(Y)
+        x.copy_(Y + draw() * float(sde._std(1.0)))
+        timesteps = torch.linspace(sde.T, self.t_eps, N).numpy()
+        for i in range(N):
+            t = timesteps[i]
+            std = float(sde._std(t))
+            for _ in range(corrector_steps):
+                # ALD (correctors.py:54-66): x <- x + step*score + sqrt(2 step) z, score = -v/std
+                step = (snr * std) ** 2 * 2
+                backbone_stage(x, t, xn, 1.0, 0.0, draw(), float(np.sqrt(np.float32(step * 2))), -step / std)
+                x, xn = xn, x
+            # reverse diffusion (predictors.py:66-71, sdes.py:118-123):
+            #   rev_f = theta dt (y - x) - G^2 score ; x_mean = x - rev_f ; x = x_mean + G z
+            th_dt, G = sde.discretize(t)
+            th_dt, G = float(th_dt), float(G)
+            last = (i == N - 1)
+            z = None if (last and denoise) else draw()
+            if last:
+                backbone_stage(x, t, x_mean, 1.0 + th_dt, -th_dt, None, 0.0, -G * G / std)
+                if not denoise:
+                    x_mean = x_mean + G * z
+            else:
+                backbone_stage(x, t, xn, 1.0 + th_dt, -th_dt, z, G, -G * G / std)
+                x, xn = xn, x
+        out = torch.empty(B * C, L, **f32)
+        fe.istft_decompress(x_mean, L, nf, out)
+        x_hat = out.reshape(B, C, L)
+        for _ in range(squeeze_dims):
+            x_hat = x_hat.squeeze(0)
+        x_hat = x_hat.to(y_in.device)
+        info = dict(orig_length=L, normfac=nf.clone().reshape(B, C, 1), undo_pad_fn=(lambda Y_, T=1 + L // 384: Y_[..., :T]),
+                    squeeze_dims=squeeze_dims)
+        return (x_hat, info) if return_preprocess_info else x_hat
+
+
+def build_scoredec(device=None):
+    """the model `config/baseline_scoredec_75s.yaml` instantiates (score_model_final.yaml + ouve_final.yaml)"""
+    from .sdes import OUVESDE
+    fm = build_flowdec("75m")
+    m = ScoreModel(OUVESDE(theta=1.5, sigma_min=0.05, sigma_max=0.82, N=30), 3e-2, backbone=fm.backbone,
+                   feature_extractor=fm.feature_extractor, sampling_rate=48000, lr=1e-4)
+    m.eval()
+    return m.to(device) if device is not None else m
 
 
 def build_flowdec(variant="75m", device=None):

@@ -171,12 +171,13 @@ def combine(pyr4, w, b, h, out):
     return out
 
 
-def output_axpy(pyr4, w_out8, base1, c1, base2, c2, coef, out, v_out=None):
+def output_axpy(pyr4, w_out8, base1, c1, base2, c2, coef, out, v_out=None, base3=None, c3=0.0):
     """w_out8: host ctypes float[8] (2x4 output-layer weights)."""
     npix = pyr4.numel() // 4
     rc = _lib.lib().fd_output_axpy(_lib.ptr(pyr4), w_out8, _lib.ptr(base1), ctypes.c_float(c1),
-                                   _lib.ptr(base2), ctypes.c_float(c2), ctypes.c_float(coef),
-                                   _lib.ptr(out), _lib.ptr(v_out), ctypes.c_size_t(npix), _lib.stream_ptr())
+                                   _lib.ptr(base2), ctypes.c_float(c2), _lib.ptr(base3), ctypes.c_float(c3),
+                                   ctypes.c_float(coef), _lib.ptr(out), _lib.ptr(v_out),
+                                   ctypes.c_size_t(npix), _lib.stream_ptr())
     _lib.check(rc, "fd_output_axpy")
     return out
 

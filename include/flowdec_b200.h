@@ -95,11 +95,13 @@ int fd_conv_in(const void* in4, const float* w, const float* bias, void* out, in
 int fd_combine(const void* pyr4, const float* w, const float* bias, const void* h, void* out,
                size_t npix, int C, fd_stream_t stream);
 /* ncsnpp.py:398 output 1x1 conv (w_out_host8 = HOST pointer to the 2x4 weights) fused with one
- * explicit ODE stage (torchdyn Euler/Midpoint step, flowdec/sampling/solvers.py:15-57):
- *   v = W_out * pyr ; out = c1*base1 + c2*base2 + coef*v   (NULL bases / out / v_out allowed) */
+ * sampler stage: torchdyn Euler/Midpoint and Heun2 (flowdec/sampling/solvers.py:15-57), the
+ * reverse-diffusion predictor (sampling/predictors.py:61-71, sdes.py:118-123) and the ALD corrector
+ * (sampling/correctors.py:54-66) are all affine in (x, y, noise, v):
+ *   v = W_out * pyr ; out = c1*base1 + c2*base2 + c3*base3 + coef*v  (NULL bases / out / v_out allowed) */
 int fd_output_axpy(const void* pyr4, const float* w_out_host8, const void* base1, float c1,
-                   const void* base2, float c2, float coef, void* out, void* v_out, size_t npix,
-                   fd_stream_t stream);
+                   const void* base2, float c2, const void* base3, float c3, float coef, void* out,
+                   void* v_out, size_t npix, fd_stream_t stream);
 /* model.py:512,530-536: out = Y + fac * (float)(sigma[f] (f64) * eps) */
 int fd_x0(const void* Y, const double* sigma, const void* eps, float fac, void* out, int B, int F, int T,
           fd_stream_t stream);

@@ -65,6 +65,26 @@ def test_enhance_vs_golden(model, N, solver):
     assert torch.equal(x2, x) and torch.equal(x3, x)
 
 
+def test_scoredec_pc_sampler_vs_golden(model):
+    """ScoreDec baseline path (ScoreModel + OUVE SDE + PC sampler) around the same backbone.
+    The untrained score network diverges (|x| ~ 1e5), so the gate is relative: SNR >= 20 dB."""
+    from flowdec_b200.model import ScoreModel
+    from flowdec_b200.sdes import OUVESDE
+    I = golden_inputs()
+    gold = torch.from_numpy(np.load(GOLD)["scoredec_pc_N2"])
+    sm = ScoreModel(OUVESDE(theta=1.5, sigma_min=0.05, sigma_max=0.82, N=30), 3e-2, backbone=model.backbone,
+                    feature_extractor=model.feature_extractor, sampling_rate=48000, lr=1e-4).cuda()
+    x = sm.enhance(I["y"], N=2, snr=0.5, noise=I["score_draws"])
+    s = snr_db(x, gold)
+    print(f"\nScoreDec PC sampler N=2: waveform SNR vs reference golden = {s:.2f} dB")
+    assert x.shape == gold.shape and s >= 20.0
+    # score = -backbone / sigma_t (model.py:613-628)
+    t = torch.tensor([0.5]).cuda()
+    sc = sm(I["X"].cuda(), I["Y"].cuda(), t)
+    v = model.backbone(I["X"].cuda(), I["Y"].cuda(), t)
+    assert torch.allclose(sc, -v / float(sm.sde._std(0.5)))
+
+
 def test_enhance_api_shapes_and_info(model):
     I = golden_inputs()
     y = I["y"]

@@ -118,10 +118,11 @@ def test_conv_in_combine_pyramid_output():
     base2 = torch.randn(B, H, W, 2)
     od = torch.empty(B, H, W, 2, device=DEV)
     vd = torch.empty(B, H, W, 2, device=DEV)
-    ops.output_axpy(add_d, w8, base.to(DEV), 0.5, base2.to(DEV), 0.25, 0.125, od, vd)
+    base3 = torch.randn(B, H, W, 2)
+    ops.output_axpy(add_d, w8, base.to(DEV), 0.5, base2.to(DEV), 0.25, 0.125, od, vd, base3=base3.to(DEV), c3=-2.0)
     v = torch.einsum("oc,bhwc->bhwo", wo, add_d.cpu())
     assert rel_l2(vd.cpu(), v) < 1e-6
-    assert rel_l2(od.cpu(), 0.5 * base + 0.25 * base2 + 0.125 * v) < 1e-6
+    assert rel_l2(od.cpu(), 0.5 * base + 0.25 * base2 - 2.0 * base3 + 0.125 * v) < 1e-6
 
 
 def test_time_embedding_matvec():

@@ -60,6 +60,13 @@ def test_enhance_vs_golden(sd, gold, N, solver):
     assert rel_l2(x, gold[f"enhance_{solver}_N{N}"]) < 1e-4
 
 
+def test_scoredec_pc_sampler_vs_golden(sd, gold):
+    I = golden_inputs()
+    with torch.no_grad():
+        x = O.score_enhance(sd, I["y"], N=2, snr=0.5, noise=I["score_draws"])
+    assert rel_l2(x, gold["scoredec_pc_N2"]) < 1e-4
+
+
 @pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present on this machine")
 def test_oracle_vs_live_reference_small():
     """cheap live pin: a 2-level, nf=16 backbone of the same family, reference vs oracle"""
