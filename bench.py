@@ -324,8 +324,16 @@ def main():
         peak, how = load_peaks()
         algo_flops_step = 2.0 * MACS_PER_FRAME * B * Tp * nfe
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        traffic, traffic_note = None, None
+        tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_note = (f"ncu dram read+write of the dominant launch shape ({tj['launch_shape']}); algorithmic "
+                            f"{tj['algorithmic_bytes_per_launch']} B; tensor pipe active {tj['tensor_pipe_active_pct_of_elapsed']} % of elapsed")
         roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
-                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_note": traffic_note,
                     "peak_source": how, "launches": len(prof), "kernel_ms_per_step": conv_ms,
                     "kernel_share_of_step": conv_ms / (ms / args.steps),
                     "algorithmic_tflop_per_step": algo_flops_step / 1e12,
