@@ -25,6 +25,8 @@ class ConvSrc(ctypes.Structure):
         ("c_begin", ctypes.c_int),
         ("c_count", ctypes.c_int),
         ("taps", ctypes.c_int),
+        ("scale_shift", ctypes.c_void_p),
+        ("ss_pitch", ctypes.c_int),
     ]
 
 

@@ -182,6 +182,7 @@ class NCSNpp(nn.Module):
         self.stats_slabs = 64
         self.fuse_stats = True     # GroupNorm partial sums produced by the conv epilogue
         self.pyramid_shift_after_gemm = True
+        self.fuse_gn_into_conv = True   # GroupNorm+SiLU applied inside the conv kernel (halo tiles)
         self.max_ctas = 0
 
     # ------------------------------------------------------------------ parameter management
@@ -233,6 +234,7 @@ class NCSNpp(nn.Module):
                     e = {}
                     cin, cout = m.in_ch, m.out_ch
                     e["w0"] = ops.pack_conv_weight([(m.Conv_0.weight.float(), 9)], self._npad(cout))
+                    e["w0_full"] = m.Conv_0.weight.float()
                     e["b0"] = m.Conv_0.bias.float().contiguous()
                     w1 = m.Conv_1.weight.float() * inv
                     if hasattr(m, "Conv_2"):
@@ -325,6 +327,14 @@ class NCSNpp(nn.Module):
             cache[k] = p
         return p
 
+    def _gn_scale_shift(self, srcs, gamma, beta, scache, name):
+        """GroupNorm statistics of the virtual concat -> per-(sample, channel) scale/shift [B, C, 2]."""
+        B, H, W = srcs[0].shape[:3]
+        C = sum(s.shape[3] for s in srcs)
+        parts = [self._partials(s, scache) for s in srcs]
+        ss = self._ws.get(name, (B, C, 2), torch.float32, srcs[0].device)
+        return ops.gn_finalize(parts, [s.shape[3] for s in srcs], H * W, gamma, beta, min(C // 4, 32), 1e-6, ss)
+
     def _gn_act(self, srcs, gamma, beta, mode, scache, name, raw_name=None):
         """a = FIR?(SiLU(GroupNorm(cat(srcs)))) as one bf16 NHWC tensor (+ FIR(cat(srcs)) if raw_name)."""
         B, H, W = srcs[0].shape[:3]
@@ -348,19 +358,35 @@ class NCSNpp(nn.Module):
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
         cin, cout = m.in_ch, m.out_ch
         assert sum(s.shape[3] for s in srcs) == cin
+        # GroupNorm+SiLU fused into the conv's operand path (halo kernel) when the tile geometry allows;
+        # otherwise (and for the FIR-resampled conv0 input) a materialised bf16 activation tensor
+        fuse = self.fuse_gn_into_conv and ops.halo_eligible(B, Ho, Wo, self._npad(cout))
         if mode != 0:
             a0, xr = self._gn_act(srcs, e["g0"], e["be0"], mode, scache, "act", raw_name="xr")
+            conv0_srcs, w0 = [(a0, 0, cin, 9)], e["w0"]
+        elif fuse:
+            ss0 = self._gn_scale_shift(srcs, e["g0"], e["be0"], scache, "gn_ss0")
+            conv0_srcs, off = [], 0
+            for sx in srcs:
+                conv0_srcs.append((sx, 0, sx.shape[3], 9, ss0, off))
+                off += sx.shape[3]
+            w0 = self._conv0_weight(e, [sx.shape[3] for sx in srcs], cout)
         else:
             a0 = self._gn_act(srcs, e["g0"], e["be0"], mode, scache, "act")
+            conv0_srcs, w0 = [(a0, 0, cin, 9)], e["w0"]
         h1 = self._ws.get("h1", (B, Ho, Wo, cout), torch.bfloat16, dev)
         scache.pop(h1.data_ptr(), None)
         st_h1 = None
         if self.fuse_stats:
             st_h1 = self._ws.get("h1_stats", (B, ops.conv_stats_slabs(Ho, Wo), cout, 2), torch.float32, dev)
-        ops.conv_igemm([(a0, 0, cin, 9)], e["w0"], tb[i], h1, self.max_ctas, stats=st_h1)
+        ops.conv_igemm(conv0_srcs, w0, tb[i], h1, self.max_ctas, stats=st_h1)
         if st_h1 is not None:
             scache[h1.data_ptr()] = self._compact_stats(st_h1, "h1_stats_c")
-        a1 = self._gn_act([h1], e["g1"], e["be1"], 0, scache, "act")
+        if fuse:
+            ss1 = self._gn_scale_shift([h1], e["g1"], e["be1"], scache, "gn_ss1")
+            conv1_main = (h1, 0, cout, 9, ss1, 0)
+        else:
+            conv1_main = (self._gn_act([h1], e["g1"], e["be1"], 0, scache, "act"), 0, cout, 9)
         scache.pop(h1.data_ptr(), None)
         if mode != 0:
             skip = [xr]
@@ -376,11 +402,26 @@ class NCSNpp(nn.Module):
             # large S: shared scratch, compacted below into a per-block buffer; small S: kept as is
             st_out = self._ws.get("rb_stats" if S > self.stats_slabs else f"rb{i}_stats_c", (B, S, cout, 2),
                                   torch.float32, dev)
-        ops.conv_igemm([(a1, 0, cout, 9)] + [(s, 0, s.shape[3], 1) for s in skip], wp, e["b1"], out,
+        ops.conv_igemm([conv1_main] + [(s, 0, s.shape[3], 1) for s in skip], wp, e["b1"], out,
                        self.max_ctas, algo_k=algo_k, stats=st_out)
         if st_out is not None:
             scache[out.data_ptr()] = self._compact_stats(st_out, f"rb{i}_stats_c")
         return out
+
+    def _conv0_weight(self, e, seg_channels, cout):
+        """Conv_0 packed for a multi-source (virtual concat) operand: K = segment > tap > channel"""
+        if len(seg_channels) == 1:
+            return e["w0"]
+        key = ("w0",) + tuple(seg_channels)
+        wp = e["w1_cache"].get(key)
+        if wp is None:
+            segs, c0 = [], 0
+            for c in seg_channels:
+                segs.append((e["w0_full"][:, c0:c0 + c].contiguous(), 9))
+                c0 += c
+            wp = ops.pack_conv_weight(segs, self._npad(cout))
+            e["w1_cache"][key] = wp
+        return wp
 
     def _compact_stats(self, st, name):
         """conv-epilogue partials [B,S,C,2] -> at most `stats_slabs` slabs (coalesced stage-1 reduce)"""

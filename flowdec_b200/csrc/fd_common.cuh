@@ -284,6 +284,42 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       : "memory");
 }
 
+// cluster-scope release/acquire pair: data written to this CTA's shared memory by ordinary
+// stores (then fence.proxy.async) is consumed by an MMA the *peer* CTA's thread issues
+__device__ __forceinline__ void mbar_arrive_remote_release_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t polls = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (((++polls) & 0xFFFu) == 0 && (clock64() - t0) > 8000000000ll) {
+      printf("flowdec_b200: cluster mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
 // In a 2-CTA cluster the shared-window address carries the CTA rank in bit 24; clearing it
 // addresses the leader's copy of the barrier (what cute::SM100_TMA_2SM_LOAD does).
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;

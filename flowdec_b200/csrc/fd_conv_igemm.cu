@@ -350,6 +350,323 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   }
 }
 
+// =================================================================================
+// "Halo" variant (CTA pairs only): 8 x 16-pixel tiles.
+//   * one A load = a 10-row x 16-column x 64-channel box that serves the THREE vertical taps of one
+//     (dw, k-slice): the tap dh just offsets the smem descriptor by (dh+1)*16 rows = 2 KB, which keeps
+//     the 1024-byte swizzle-atom alignment.  L2->smem traffic of A drops 2.4x versus one box per tap.
+//   * optional in-shared-memory transform (XF): the box holds the RAW res-block tensor and four
+//     helper warps apply GroupNorm affine + SiLU in place (zeroing out-of-image positions, which is
+//     the conv's zero padding of the ACTIVATED tensor) before the MMAs read it.  This removes the
+//     separate GroupNorm+SiLU pass and its bf16 round trip through HBM (layerspp.py:253,274 fused
+//     into the operand path of Conv_0 / Conv_1).
+//   * weights: a separate ring of [N/2 x 64] tiles, one per (tap, k-slice).
+// warps: 0 producer (A and B rings), 1 MMA issuer (leader CTA), 2-5 epilogue, 6-9 transform.
+// =================================================================================
+constexpr int kHaloRows = 10;
+constexpr int kHaloW = 16;
+constexpr int kHaloBytes = kHaloRows * kHaloW * 128;   // 20480
+constexpr int kHaloTileH = 8;
+
+struct HaloParams {
+  CUtensorMap a_map[kMaxSeg];
+  CUtensorMap b_map;
+  CUtensorMap out_map;
+  int nseg;
+  int seg_kslices[kMaxSeg];
+  int seg_taps[kMaxSeg];
+  int seg_kbase[kMaxSeg];        // K offset of the segment inside the packed weight
+  int seg_cin[kMaxSeg];          // channels consumed by the segment
+  const float* seg_ss[kMaxSeg];  // GroupNorm scale/shift [B][ss_pitch][2] (+ channel offset) or nullptr = raw
+  int seg_ss_pitch[kMaxSeg];
+  int seg_ss_off[kMaxSeg];       // offset of the segment's channels in the smem scale/shift table
+  int B, H, W;
+  int tiles_h, tiles_w, num_tiles;
+  const float* bias;
+  float* stats;
+};
+
+template <int N>
+struct HaloCfg {
+  static constexpr int kStagesA = 3;
+  static constexpr int kStagesB = 6;
+  static constexpr int kBBytes = (N / 2) * kSliceK * 2;
+  static constexpr int kOutBytes = 2 * kTileM * 128;
+  static constexpr int kSsFloats = 2 * 512;   // scale/shift of up to 512 transformed channels
+  static constexpr int kTmemCols = (2 * N <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = 1024 + kStagesA * kHaloBytes + kStagesB * kBBytes + kOutBytes + N * 4 +
+                                    kSsFloats * 4 + 512;
+};
+
+template <int N, bool XF>
+__global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  using Cfg = HaloCfg<N>;
+  constexpr int SA = Cfg::kStagesA, SB = Cfg::kStagesB, B_BYTES = Cfg::kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + SA * kHaloBytes;
+  uint8_t* sOut = sB + SB * B_BYTES;
+  float* sBias = reinterpret_cast<float*>(sOut + Cfg::kOutBytes);
+  float* sSS = sBias + N;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSS + Cfg::kSsFloats);
+  uint64_t* fullA = bars;                 // [SA] TMA landed (XF: local, consumed by the transform warps)
+  uint64_t* readyA = bars + SA;           // [SA] operand ready for the MMA (leader CTA's copy is used)
+  uint64_t* emptyA = bars + 2 * SA;       // [SA]
+  uint64_t* fullB = bars + 3 * SA;        // [SB] (leader's copy)
+  uint64_t* emptyB = bars + 3 * SA + SB;  // [SB]
+  uint64_t* tfull_bar = bars + 3 * SA + 2 * SB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader_cta = (rank == 0);
+
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sBias[i] = p.bias ? p.bias[i] : 0.0f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&readyA[s], XF ? 8 : 2);   // XF: 4 transform warps of each CTA; else expect_tx + peer arrive
+      mbar_init(&emptyA[s], 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(&fullB[s], 2);
+      mbar_init(&emptyB[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 256);
+    }
+    fence_mbar_init();
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.a_map[s]);
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.out_map);
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tile_first = static_cast<int>((blockIdx.x >> 1) * 2 + rank);
+  const int tile_stride = static_cast<int>(gridDim.x);
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer (A halo + B rings)
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * kHaloTileH;
+        const int w0 = (rem % p.tiles_w) * kHaloW;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int taps = p.seg_taps[s];
+          const int ndw = (taps == 9) ? 3 : 1;
+          for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
+            for (int di = 0; di < ndw; ++di) {
+              const int dw = (taps == 9) ? di - 1 : 0;
+              mbar_wait(&emptyA[sa], pa ^ 1u);
+              if (XF) {
+                mbar_expect_tx(&fullA[sa], kHaloBytes);
+                tma_load_4d(sA + sa * kHaloBytes, &p.a_map[s], &fullA[sa], ks * kSliceK, w0 + dw, h0 - 1, n);
+              } else {
+                if (leader_cta) mbar_expect_tx(&readyA[sa], 2 * kHaloBytes);
+                else mbar_arrive_remote(&readyA[sa], 0);
+                tma_load_4d_2sm(sA + sa * kHaloBytes, &p.a_map[s], &readyA[sa], ks * kSliceK, w0 + dw, h0 - 1, n);
+              }
+              if (++sa == SA) { sa = 0; pa ^= 1u; }
+              for (int dhi = 0; dhi < ndw; ++dhi) {
+                const int tap = (taps == 9) ? dhi * 3 + di : 0;
+                const int kcol = p.seg_kbase[s] + tap * p.seg_cin[s] + ks * kSliceK;
+                mbar_wait(&emptyB[sb], pb ^ 1u);
+                if (leader_cta) mbar_expect_tx(&fullB[sb], 2 * B_BYTES);
+                else mbar_arrive_remote(&fullB[sb], 0);
+                tma_load_2d_2sm(sB + sb * B_BYTES, &p.b_map, &fullB[sb], kcol, static_cast<int>(rank) * (N / 2));
+                if (++sb == SB) { sb = 0; pb ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (leader CTA)
+    if (lane == 0 && leader_cta) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kTileM, N);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int acc = 0, issued = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
+        ++issued;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * N);
+        uint32_t first = 1;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int ndw = (p.seg_taps[s] == 9) ? 3 : 1;
+          const int stages = p.seg_kslices[s] * ndw;
+          for (int st = 0; st < stages; ++st) {
+            if (XF) mbar_wait_acquire_cluster(&readyA[sa], pa); else mbar_wait(&readyA[sa], pa);
+            tc_fence_after_sync();
+            const uint32_t a_base = smem_u32(sA + sa * kHaloBytes);
+            for (int dhi = 0; dhi < ndw; ++dhi) {
+              const int dh = (ndw == 3) ? dhi - 1 : 0;
+              mbar_wait(&fullB[sb], pb);
+              tc_fence_after_sync();
+              const uint64_t da = umma_desc_k_sw128(a_base + static_cast<uint32_t>((dh + 1) * kHaloW * 128));
+              const uint64_t db = umma_desc_k_sw128(smem_u32(sB + sb * B_BYTES));
+#pragma unroll
+              for (int k = 0; k < kSliceK / 16; ++k) {
+                umma_bf16_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                              idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit_2sm(&emptyB[sb]);
+              if (++sb == SB) { sb = 0; pb ^= 1u; }
+            }
+            umma_commit_2sm(&emptyA[sa]);
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
+          }
+        }
+        umma_commit_2sm(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (issued > 0)
+        for (int j = (issued >= 2 ? issued - 2 : issued - 1); j < issued; ++j)
+          mbar_wait(&tempty_bar[j & 1], static_cast<uint32_t>((j >> 1) & 1));
+    }
+  } else if (warp < 6) {
+    // ---------------------------------------------------------------- epilogue (as conv_igemm_kernel)
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    const bool leader = (threadIdx.x == 64);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * kHaloTileH;
+      const int w0 = (rem % p.tiles_w) * kHaloW;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * N);
+      constexpr int kChunks = N / 64;
+      const int slab = rem * 4 + ew;
+      float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * (tiles_per_img * 4) + slab) * N) * 2 : nullptr;
+#pragma unroll 1
+      for (int ch = 0; ch < kChunks; ++ch) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(t_row + ch * 64, v0);
+        tmem_ld_32x32b_x32(t_row + ch * 64 + 32, v1);
+        tmem_ld_wait();
+        if (ch == kChunks - 1) {
+          tc_fence_before_sync();
+          mbar_arrive_remote(&tempty_bar[acc], 0);
+        }
+        uint8_t* stg = sOut + (ch & 1) * (kTileM * 128);
+        if (leader) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        const float* bs = sBias + ch * 64;
+        uint8_t* rowp = stg + row * 128;
+        epilogue_half(v0, bs, rowp, row, 0, stat_row ? stat_row + (ch * 64) * 2 : nullptr, lane);
+        epilogue_half(v1, bs + 32, rowp, row, 4, stat_row ? stat_row + (ch * 64 + 32) * 2 : nullptr, lane);
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (leader) {
+          tma_store_4d(&p.out_map, stg, ch * 64, w0, h0, n);
+          tma_store_commit();
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (leader) tma_store_wait_all<0>();
+  } else if (XF) {
+    // ---------------------------------------------------------------- transform warps (6..9)
+    const int tx = threadIdx.x - 192;       // 0..127
+    const int j = tx & 7;                   // logical 16-byte chunk = channels j*8 .. j*8+7 of the slice
+    const int ww = tx >> 3;                 // halo column owned by this thread (0..15)
+    const int slot = (j ^ (ww & 7)) << 4;   // physical chunk position (rows r = ww + 16*hh share r & 7)
+    int sa = 0;
+    uint32_t pa = 0;
+    int cur_n = -1;
+    for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * kHaloTileH;
+      const int w0 = (rem % p.tiles_w) * kHaloW;
+      if (n != cur_n) {
+        // (re)load this sample's GroupNorm scale/shift for every transformed segment
+        named_bar_sync(3, 128);
+        for (int s = 0; s < p.nseg; ++s) {
+          if (p.seg_ss[s] == nullptr) continue;
+          const float2* src = reinterpret_cast<const float2*>(p.seg_ss[s]) + static_cast<size_t>(n) * p.seg_ss_pitch[s];
+          float2* dst = reinterpret_cast<float2*>(sSS) + p.seg_ss_off[s];
+          for (int c = tx; c < p.seg_cin[s]; c += 128) dst[c] = src[c];
+        }
+        named_bar_sync(3, 128);
+        cur_n = n;
+      }
+      for (int s = 0; s < p.nseg; ++s) {
+        const int ndw = (p.seg_taps[s] == 9) ? 3 : 1;
+        const bool xf = p.seg_ss[s] != nullptr;
+        for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
+          float sc[8], sh[8];
+          if (xf) {
+            const float4* t4 = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(sSS) + p.seg_ss_off[s] +
+                                                               ks * kSliceK + j * 8);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 q = t4[e];
+              sc[2 * e] = q.x; sh[2 * e] = q.y; sc[2 * e + 1] = q.z; sh[2 * e + 1] = q.w;
+            }
+          }
+          for (int di = 0; di < ndw; ++di) {
+            const int dw = (ndw == 3) ? di - 1 : 0;
+            mbar_wait(&fullA[sa], pa);
+            if (xf) {
+              uint8_t* base = sA + sa * kHaloBytes + ww * 128 + slot;
+              const bool col_ok = (w0 + dw + ww >= 0) && (w0 + dw + ww < p.W);
+#pragma unroll
+              for (int hh = 0; hh < kHaloRows; ++hh) {
+                uint4* ptr = reinterpret_cast<uint4*>(base + hh * (kHaloW * 128));
+                const int hy = h0 - 1 + hh;
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (col_ok && hy >= 0 && hy < p.H) {
+                  const uint4 r = *ptr;
+                  const float2 a0 = unpack_bf16x2(r.x), a1 = unpack_bf16x2(r.y), a2 = unpack_bf16x2(r.z),
+                               a3 = unpack_bf16x2(r.w);
+                  q.x = pack_bf16x2(silu_fast(fmaf(a0.x, sc[0], sh[0])), silu_fast(fmaf(a0.y, sc[1], sh[1])));
+                  q.y = pack_bf16x2(silu_fast(fmaf(a1.x, sc[2], sh[2])), silu_fast(fmaf(a1.y, sc[3], sh[3])));
+                  q.z = pack_bf16x2(silu_fast(fmaf(a2.x, sc[4], sh[4])), silu_fast(fmaf(a2.y, sc[5], sh[5])));
+                  q.w = pack_bf16x2(silu_fast(fmaf(a3.x, sc[6], sh[6])), silu_fast(fmaf(a3.y, sc[7], sh[7])));
+                }
+                *ptr = q;
+              }
+              fence_proxy_async_smem();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote_release_cluster(&readyA[sa], 0);
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+}
+
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
@@ -449,22 +766,55 @@ static int launch_conv(const ConvParams& p, int max_ctas, cudaStream_t stream) {
   return check_launch("fd_conv2d_igemm");
 }
 
+template <int N, bool XF>
+static int launch_halo(const HaloParams& p, int max_ctas, cudaStream_t stream) {
+  auto kern = conv_halo_kernel<N, XF>;
+  using Cfg = HaloCfg<N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    FD_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+               cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int grid = std::min(p.num_tiles, max_ctas > 0 ? max_ctas : device_sm_count()) & ~1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(XF ? 320 : 192);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  FD_REQUIRE(e == cudaSuccess, "fd_conv2d_igemm(halo): launch failed: %s", cudaGetErrorString(e));
+  return check_launch("fd_conv2d_igemm(halo)");
+}
+
 }  // namespace fd
 
 // ---------------------------------------------------------------------------------
 // C ABI (declared in include/flowdec_b200.h)
 // ---------------------------------------------------------------------------------
 struct fd_conv_src {
-  const void* ptr;  // bf16 NHWC [B,H,W,C]
-  int C;            // channel pitch of the tensor
-  int c_begin;      // first channel consumed
-  int c_count;      // channels consumed (multiple of 64)
-  int taps;         // 1 or 9
+  const void* ptr;           // bf16 NHWC [B,H,W,C]
+  int C;                     // channel pitch of the tensor
+  int c_begin;               // first channel consumed
+  int c_count;               // channels consumed (multiple of 64)
+  int taps;                  // 1 or 9
+  const float* scale_shift;  // nullptr, or GroupNorm scale/shift [B][ss_pitch][2] of THIS source's first
+                             // consumed channel: the kernel applies SiLU(x*scale+shift) to the operand
+  int ss_pitch;              // channels per sample in that table (the virtual concat's width)
 };
 
 extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot,
                                const float* bias, void* out, int out_is_f32, int cout, int npad,
-                               int B, int H, int W, float* stats, int max_ctas, int cta_pairs, cudaStream_t stream) {
+                               int B, int H, int W, float* stats, int max_ctas, int flags, cudaStream_t stream) {
   using namespace fd;
   FD_REQUIRE(nsrc >= 1 && nsrc <= kMaxSeg, "fd_conv2d_igemm: nsrc=%d out of range [1,%d]", nsrc, kMaxSeg);
   FD_REQUIRE(npad == 16 || npad == 48 || npad == 128 || npad == 256, "fd_conv2d_igemm: npad=%d unsupported", npad);
@@ -490,8 +840,53 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
       return 1;
   }
   FD_REQUIRE(ksum == ktot, "fd_conv2d_igemm: packed K=%d does not match segments (%d)", ktot, ksum);
+  bool any_xf = false;
+  for (int s = 0; s < nsrc; ++s) any_xf = any_xf || (srcs[s].scale_shift != nullptr);
+  {
+    // "halo" kernel: 8x16 tiles, A box shared by the three vertical taps, optional fused GN+SiLU
+    const bool halo_ok = !out_is_f32 && (flags & 1) && (flags & 2) && (npad == 128 || npad == 256) &&
+                         (W % kHaloW == 0) && (H % kHaloTileH == 0) &&
+                         ((static_cast<long long>(B) * (H / kHaloTileH) * (W / kHaloW)) % 2 == 0);
+    FD_REQUIRE(halo_ok || !any_xf, "fd_conv2d_igemm: fused GroupNorm+SiLU needs the halo kernel "
+               "(bf16 out, flags 3, W %% 16 == 0, H %% 8 == 0, even tile count)");
+    if (halo_ok) {
+      HaloParams hp;
+      memset(&hp, 0, sizeof(hp));
+      hp.nseg = nsrc;
+      int kb = 0, ssoff = 0;
+      for (int s = 0; s < nsrc; ++s) {
+        hp.seg_kslices[s] = srcs[s].c_count / kSliceK;
+        hp.seg_taps[s] = srcs[s].taps;
+        hp.seg_kbase[s] = kb;
+        hp.seg_cin[s] = srcs[s].c_count;
+        hp.seg_ss[s] = srcs[s].scale_shift;
+        hp.seg_ss_pitch[s] = srcs[s].ss_pitch;
+        hp.seg_ss_off[s] = ssoff;
+        if (srcs[s].scale_shift) ssoff += srcs[s].c_count;
+        kb += srcs[s].c_count * srcs[s].taps;
+        if (make_nhwc_map(&hp.a_map[s], srcs[s].ptr, B, H, W, srcs[s].C, srcs[s].c_begin, srcs[s].c_count,
+                          kHaloRows, kHaloW))
+          return 1;
+      }
+      FD_REQUIRE(ssoff <= 512, "fd_conv2d_igemm: at most 512 transformed channels (got %d)", ssoff);
+      if (make_weight_map(&hp.b_map, wpacked, npad, ktot, npad / 2)) return 1;
+      FD_REQUIRE(cout == npad, "fd_conv2d_igemm: bf16 output needs cout == npad");
+      if (make_nhwc_map(&hp.out_map, out, B, H, W, cout, 0, cout, kHaloTileH, kHaloW)) return 1;
+      hp.B = B;
+      hp.H = H;
+      hp.W = W;
+      hp.tiles_h = H / kHaloTileH;
+      hp.tiles_w = W / kHaloW;
+      hp.num_tiles = B * hp.tiles_h * hp.tiles_w;
+      hp.bias = bias;
+      hp.stats = stats;
+      if (npad == 256) return any_xf ? launch_halo<256, true>(hp, max_ctas, stream)
+                                     : launch_halo<256, false>(hp, max_ctas, stream);
+      return any_xf ? launch_halo<128, true>(hp, max_ctas, stream) : launch_halo<128, false>(hp, max_ctas, stream);
+    }
+  }
   // CTA pairs (cta_group::2, M = 256 per MMA) for the bf16-output tiles when the tile count is even
-  const bool pair = !out_is_f32 && (cta_pairs != 0) && (((B * (H / bh) * (W / bw)) & 1) == 0) &&
+  const bool pair = !out_is_f32 && ((flags & 1) != 0) && (((B * (H / bh) * (W / bw)) & 1) == 0) &&
                     (B * (H / bh) * (W / bw) >= 2);
   if (make_weight_map(&p.b_map, wpacked, npad, ktot, pair ? npad / 2 : npad)) return 1;
   p.B = B;

@@ -11,6 +11,14 @@ from . import _lib
 
 # CTA-pair (cta_group::2) convolution tiles; tests flip this to compare both MMA variants
 CTA_PAIRS = True
+# 8x16 "halo" tiles (A box shared by the three vertical taps; needed for fused GroupNorm+SiLU operands)
+HALO_TILES = True
+
+
+def halo_eligible(B, H, W, npad):
+    """mirror of the dispatch rule in fd_conv2d_igemm"""
+    return (CTA_PAIRS and HALO_TILES and npad in (128, 256) and W % 16 == 0 and H % 8 == 0
+            and (B * (H // 8) * (W // 16)) % 2 == 0)
 
 # when set to a list, conv_igemm appends (start_event, end_event, algorithmic_flops) per launch
 # (bench.py's roofline leg; events are recorded on the launching stream)
@@ -42,18 +50,29 @@ def conv_stats_slabs(H, W):
 
 
 def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None, algo_cout=None):
-    """srcs: list of (tensor NHWC bf16, c_begin, c_count, taps). out: NHWC bf16 [.., npad] or fp32 [.., cout<=16]."""
+    """srcs: list of (tensor NHWC bf16, c_begin, c_count, taps[, scale_shift, channel_offset]).
+    With scale_shift (fp32 [B, Cvirt, 2]) the kernel consumes SiLU(x*scale+shift) instead of x.
+    out: NHWC bf16 [.., npad] or fp32 [.., cout]."""
     L = _lib.lib()
     n = len(srcs)
     arr = (_lib.ConvSrc * n)()
     B, H, W = srcs[0][0].shape[:3]
-    for i, (t, c0, cc, taps) in enumerate(srcs):
+    for i, src in enumerate(srcs):
+        t, c0, cc, taps = src[:4]
         assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape[:3] == (B, H, W)
         arr[i].ptr = t.data_ptr()
         arr[i].C = t.shape[3]
         arr[i].c_begin = c0
         arr[i].c_count = cc
         arr[i].taps = taps
+        if len(src) > 4 and src[4] is not None:
+            ss, ch_off = src[4], src[5]          # fp32 [B, Cvirt, 2], channel offset of this source in it
+            assert ss.dtype == torch.float32 and ss.is_contiguous() and ss.shape[0] == B
+            arr[i].scale_shift = ss.data_ptr() + ch_off * 8
+            arr[i].ss_pitch = ss.shape[1]
+        else:
+            arr[i].scale_shift = None
+            arr[i].ss_pitch = 0
     npad, ktot = wpacked.shape
     out_f32 = out.dtype == torch.float32
     if PROFILE is not None:
@@ -61,13 +80,13 @@ def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None, al
         e0.record()
     rc = L.fd_conv2d_igemm(arr, n, _lib.ptr(wpacked), ktot, _lib.ptr(bias), _lib.ptr(out),
                            int(out_f32), out.shape[3], npad, B, H, W, _lib.ptr(stats), max_ctas,
-                           int(CTA_PAIRS), _lib.stream_ptr())
+                           int(CTA_PAIRS) | (2 if HALO_TILES else 0), _lib.stream_ptr())
     _lib.check(rc, "fd_conv2d_igemm")
     if PROFILE is not None:
         e1.record()
         # algorithmic FLOPs: real output channels, and K without the identity-skip segment that
         # stands in for the res-block's "+ x" (an implementation device, not reference arithmetic)
-        k_algo = sum(cc * taps for (_, _, cc, taps) in srcs)
+        k_algo = sum(src[2] * src[3] for src in srcs)
         if algo_k is not None:
             k_algo = algo_k
         PROFILE.append((e0, e1, 2.0 * B * H * W * (algo_cout or out.shape[3]) * k_algo))

@@ -35,11 +35,15 @@ int fd_abi_version(void);
  * layerspp.py:235,243,245 and ncsnpp.py:218,230) including the res-block's skip path and
  * (x + h)/sqrt(2) (layerspp.py:278-284), which are folded into extra K segments. */
 struct fd_conv_src {
-  const void* ptr; /* bf16 NHWC [B,H,W,C] */
-  int C;           /* channel pitch of the tensor */
-  int c_begin;     /* first channel consumed (multiple of 8) */
-  int c_count;     /* channels consumed (multiple of 64) */
-  int taps;        /* 9 = 3x3 zero-padded, 1 = 1x1 */
+  const void* ptr;          /* bf16 NHWC [B,H,W,C] */
+  int C;                    /* channel pitch of the tensor */
+  int c_begin;              /* first channel consumed (multiple of 8) */
+  int c_count;              /* channels consumed (multiple of 64) */
+  int taps;                 /* 9 = 3x3 zero-padded, 1 = 1x1 */
+  const float* scale_shift; /* NULL, or GroupNorm scale/shift fp32 [B][ss_pitch][2] positioned at this
+                               source's first consumed channel: the kernel feeds SiLU(x*scale+shift)
+                               (zero outside the image) to the MMA instead of x (layerspp.py:253,274) */
+  int ss_pitch;             /* channels per sample in that table (width of the virtual concat) */
 };
 /* out[b,h,w,o] = bias[o] + sum_seg sum_tap sum_c src_seg[b,h+dh,w+dw,c] * wpacked[o, k(seg,tap,c)]
  * wpacked: bf16 [npad, ktot], K-major, k ordered segment-major, then tap (kh-major), then channel.
@@ -50,11 +54,13 @@ struct fd_conv_src {
  * stats (bf16 output only, may be NULL): GroupNorm partial sums of the OUTPUT, fp32
  * [B, S, cout, 2] with S = 4 * H*W/128 slabs (one per epilogue warp and tile), consumed by
  * fd_gn_finalize — the statistics pass of the next GroupNorm fused into this conv's epilogue.
- * max_ctas: 0 = one persistent CTA per SM.  cta_pairs != 0: CTA pairs (cta_group::2, 256-row MMAs,
- * weight tile split across the pair) when the tile count is even; 0 = single-CTA MMAs. */
+ * max_ctas: 0 = one persistent CTA per SM.  flags bit 0: CTA pairs (cta_group::2, 256-row MMAs, weight
+ * tile split across the pair) when the tile count is even; bit 1: 8x16-pixel "halo" tiles (one A box per
+ * (dw, k-slice) shared by the three vertical taps) when W % 16 == 0 and H % 8 == 0 — required for
+ * sources with scale_shift != NULL (GroupNorm+SiLU fused into the operand path). */
 int fd_conv2d_igemm(const struct fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot,
                     const float* bias, void* out, int out_is_f32, int cout, int npad, int B, int H,
-                    int W, float* stats, int max_ctas, int cta_pairs, fd_stream_t stream);
+                    int W, float* stats, int max_ctas, int flags, fd_stream_t stream);
 
 /* ---- GroupNorm + SiLU + FIR resampling ------------------------------------------------------
  * replace nn.GroupNorm / nn.SiLU (layerspp.py:229,241,253,274; ncsnpp.py:216,228) and

@@ -14,14 +14,15 @@ from flowdec_b200.ops import conv_igemm, pack_conv_weight
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[True, False], ids=["cta_pair", "single_cta"])
+@pytest.fixture(autouse=True, params=[(True, True), (True, False), (False, False)],
+                ids=["halo_pair", "cta_pair", "single_cta"])
 def _mma_variant(request):
-    """every conv test runs with cta_group::2 pairs and with single-CTA MMAs"""
+    """every conv test runs with 8x16 halo tiles (CTA pairs), plain CTA pairs and single-CTA MMAs"""
     from flowdec_b200 import ops
-    old = ops.CTA_PAIRS
-    ops.CTA_PAIRS = request.param
+    old = (ops.CTA_PAIRS, ops.HALO_TILES)
+    ops.CTA_PAIRS, ops.HALO_TILES = request.param
     yield
-    ops.CTA_PAIRS = old
+    ops.CTA_PAIRS, ops.HALO_TILES = old
 
 
 def _ref_conv(x_nhwc_bf16, w_oihw_bf16, bias):
@@ -154,3 +155,35 @@ def test_pyramid_conv_gemm_first_shift_after():
     assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-4
     ref2 = ref + O.fir_up2(lo.cpu().permute(0, 3, 1, 2)).permute(0, 2, 3, 1).to(dev)
     assert (out2 - ref2).abs().max().item() <= 1e-4 * ref2.abs().max().item() + 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2,Cout", [(1, 16, 16, 64, 0, 256), (2, 32, 48, 256, 0, 256), (2, 24, 32, 256, 64, 256),
+                                              (1, 96, 32, 128, 256, 128), (3, 8, 64, 256, 256, 256)])
+def test_conv_fused_groupnorm_silu_operand(B, H, W, C1, C2, Cout):
+    """halo kernel with scale_shift: conv(SiLU(x*scale+shift)) incl. zero padding of the ACTIVATED
+    tensor, over a virtual concat of two raw sources, plus a raw 1x1 skip segment."""
+    from flowdec_b200 import ops
+    if not (ops.CTA_PAIRS and ops.HALO_TILES):
+        pytest.skip("fused operand transform exists in the halo kernel only")
+    torch.manual_seed(6)
+    dev = "cuda"
+    C = C1 + C2
+    x1 = (torch.randn(B, H, W, C1, device=dev) * 1.3 + 0.2).to(torch.bfloat16)
+    x2 = (torch.randn(B, H, W, C2, device=dev) * 0.7).to(torch.bfloat16) if C2 else None
+    ss = torch.empty(B, C, 2, device=dev)
+    ss[..., 0] = 0.5 + torch.rand(B, C, device=dev)
+    ss[..., 1] = 0.3 * torch.randn(B, C, device=dev)
+    w = (torch.randn(Cout, C, 3, 3, device=dev) / (3 * C ** 0.5)).to(torch.bfloat16)
+    w2 = (torch.randn(Cout, C1, 1, 1, device=dev) / C1 ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, device=dev)
+    segs = [(w[:, :C1], 9)] + ([(w[:, C1:], 9)] if C2 else []) + [(w2, 1)]
+    wp = pack_conv_weight(segs, npad=Cout)
+    srcs = [(x1, 0, C1, 9, ss, 0)] + ([(x2, 0, C2, 9, ss, C1)] if C2 else []) + [(x1, 0, C1, 1)]
+    out = torch.empty(B, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    conv_igemm(srcs, wp, b, out)
+    torch.cuda.synchronize()
+    xc = torch.cat([x1, x2], -1).float() if C2 else x1.float()
+    a = F.silu(xc * ss[:, None, None, :, 0] + ss[:, None, None, :, 1]).to(torch.bfloat16)
+    ref = _ref_conv(a, w, b) + _ref_conv(x1, w2, None)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 1.5e-2 * ref.abs().max().item() + 1e-3, err
