@@ -200,6 +200,16 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+// Same layout, arbitrary stride between 8-row groups.  Measured on B200 (tools/umma_probe.py): the
+// 128B swizzle is a pure function of the shared-memory ADDRESS bits, so a descriptor may start at any
+// 128-byte-aligned row of a TMA-written tile (base_offset stays 0) and use any SBO that is a multiple
+// of 128 B; logical row m then reads tile row  start_row + (m/8)*(SBO/128) + m%8.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  const uint32_t lo = (smem_addr >> 4) & 0x3FFFu;
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |

@@ -351,22 +351,26 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
 }
 
 // =================================================================================
-// "Halo" variant (CTA pairs only): 8 x 16-pixel tiles.
-//   * one A load = a 10-row x 16-column x 64-channel box that serves the THREE vertical taps of one
-//     (dw, k-slice): the tap dh just offsets the smem descriptor by (dh+1)*16 rows = 2 KB, which keeps
-//     the 1024-byte swizzle-atom alignment.  L2->smem traffic of A drops 2.4x versus one box per tap.
-//   * optional in-shared-memory transform (XF): the box holds the RAW res-block tensor and four
-//     helper warps apply GroupNorm affine + SiLU in place (zeroing out-of-image positions, which is
-//     the conv's zero padding of the ACTIVATED tensor) before the MMAs read it.  This removes the
-//     separate GroupNorm+SiLU pass and its bf16 round trip through HBM (layerspp.py:253,274 fused
-//     into the operand path of Conv_0 / Conv_1).
-//   * weights: a separate ring of [N/2 x 64] tiles, one per (tap, k-slice).
+// "Halo" variant (CTA pairs only): 16 x 8-pixel tiles, ONE A load per k-slice for all nine taps.
+//   The A stage is an 18-row x 10-column x 64-channel box (rows of the smem tile = halo pixels at a
+//   dense 10-pixel pitch).  Because the UMMA 128B swizzle is address-based (tools/umma_probe.py), the
+//   operand of tap (dh, dw) is just a descriptor into that box: start row (1+dh)*10 + (1+dw), stride
+//   between 8-row groups (= output rows) 10 rows = 1280 B.  L2->smem traffic of A drops 6.3x.
+//   Optional in-shared-memory transform (XF): the box holds the RAW res-block tensor and four helper
+//   warps apply GroupNorm affine + SiLU in place ONCE per k-slice (zeroing out-of-image positions =
+//   the conv's zero padding of the ACTIVATED tensor) before the 36 MMAs read it.  This removes the
+//   separate GroupNorm+SiLU pass and its bf16 round trip through HBM (layerspp.py:253,274 fused into
+//   the operand path of Conv_0 / Conv_1).
+//   Weights: a separate ring of [N/2 x 64] tiles, one per (tap, k-slice).
 // warps: 0 producer (A and B rings), 1 MMA issuer (leader CTA), 2-5 epilogue, 6-9 transform.
 // =================================================================================
-constexpr int kHaloRows = 10;
-constexpr int kHaloW = 16;
-constexpr int kHaloBytes = kHaloRows * kHaloW * 128;   // 20480
-constexpr int kHaloTileH = 8;
+constexpr int kHaloRows = 18;
+constexpr int kHaloCols = 10;
+constexpr int kHaloTileH = 16;
+constexpr int kHaloTileW = 8;
+constexpr int kHaloPix = kHaloRows * kHaloCols;          // 180 smem rows of 128 B
+constexpr int kHaloTxBytes = kHaloPix * 128;             // 23040 bytes land per stage
+constexpr int kHaloStageBytes = 23552;                   // stage pitch, multiple of 1024
 
 struct HaloParams {
   CUtensorMap a_map[kMaxSeg];
@@ -394,7 +398,7 @@ struct HaloCfg {
   static constexpr int kOutBytes = 2 * kTileM * 128;
   static constexpr int kSsFloats = 2 * 512;   // scale/shift of up to 512 transformed channels
   static constexpr int kTmemCols = (2 * N <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = 1024 + kStagesA * kHaloBytes + kStagesB * kBBytes + kOutBytes + N * 4 +
+  static constexpr int kSmemBytes = 1024 + kStagesA * kHaloStageBytes + kStagesB * kBBytes + kOutBytes + N * 4 +
                                     kSsFloats * 4 + 512;
 };
 
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = sA + SA * kHaloBytes;
+  uint8_t* sB = sA + SA * kHaloStageBytes;
   uint8_t* sOut = sB + SB * B_BYTES;
   float* sBias = reinterpret_cast<float*>(sOut + Cfg::kOutBytes);
   float* sSS = sBias + N;
@@ -463,32 +467,27 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
         const int n = tile / tiles_per_img;
         const int rem = tile - n * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * kHaloTileH;
-        const int w0 = (rem % p.tiles_w) * kHaloW;
+        const int w0 = (rem % p.tiles_w) * kHaloTileW;
         for (int s = 0; s < p.nseg; ++s) {
-          const int taps = p.seg_taps[s];
-          const int ndw = (taps == 9) ? 3 : 1;
+          const int ntap = p.seg_taps[s];
           for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
-            for (int di = 0; di < ndw; ++di) {
-              const int dw = (taps == 9) ? di - 1 : 0;
-              mbar_wait(&emptyA[sa], pa ^ 1u);
-              if (XF) {
-                mbar_expect_tx(&fullA[sa], kHaloBytes);
-                tma_load_4d(sA + sa * kHaloBytes, &p.a_map[s], &fullA[sa], ks * kSliceK, w0 + dw, h0 - 1, n);
-              } else {
-                if (leader_cta) mbar_expect_tx(&readyA[sa], 2 * kHaloBytes);
-                else mbar_arrive_remote(&readyA[sa], 0);
-                tma_load_4d_2sm(sA + sa * kHaloBytes, &p.a_map[s], &readyA[sa], ks * kSliceK, w0 + dw, h0 - 1, n);
-              }
-              if (++sa == SA) { sa = 0; pa ^= 1u; }
-              for (int dhi = 0; dhi < ndw; ++dhi) {
-                const int tap = (taps == 9) ? dhi * 3 + di : 0;
-                const int kcol = p.seg_kbase[s] + tap * p.seg_cin[s] + ks * kSliceK;
-                mbar_wait(&emptyB[sb], pb ^ 1u);
-                if (leader_cta) mbar_expect_tx(&fullB[sb], 2 * B_BYTES);
-                else mbar_arrive_remote(&fullB[sb], 0);
-                tma_load_2d_2sm(sB + sb * B_BYTES, &p.b_map, &fullB[sb], kcol, static_cast<int>(rank) * (N / 2));
-                if (++sb == SB) { sb = 0; pb ^= 1u; }
-              }
+            mbar_wait(&emptyA[sa], pa ^ 1u);
+            if (XF) {
+              mbar_expect_tx(&fullA[sa], kHaloTxBytes);
+              tma_load_4d(sA + sa * kHaloStageBytes, &p.a_map[s], &fullA[sa], ks * kSliceK, w0 - 1, h0 - 1, n);
+            } else {
+              if (leader_cta) mbar_expect_tx(&readyA[sa], 2 * kHaloTxBytes);
+              else mbar_arrive_remote(&readyA[sa], 0);
+              tma_load_4d_2sm(sA + sa * kHaloStageBytes, &p.a_map[s], &readyA[sa], ks * kSliceK, w0 - 1, h0 - 1, n);
+            }
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
+            for (int tap = 0; tap < ntap; ++tap) {
+              const int kcol = p.seg_kbase[s] + tap * p.seg_cin[s] + ks * kSliceK;
+              mbar_wait(&emptyB[sb], pb ^ 1u);
+              if (leader_cta) mbar_expect_tx(&fullB[sb], 2 * B_BYTES);
+              else mbar_arrive_remote(&fullB[sb], 0);
+              tma_load_2d_2sm(sB + sb * B_BYTES, &p.b_map, &fullB[sb], kcol, static_cast<int>(rank) * (N / 2));
+              if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
           }
         }
@@ -509,17 +508,19 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * N);
         uint32_t first = 1;
         for (int s = 0; s < p.nseg; ++s) {
-          const int ndw = (p.seg_taps[s] == 9) ? 3 : 1;
-          const int stages = p.seg_kslices[s] * ndw;
-          for (int st = 0; st < stages; ++st) {
+          const int ntap = p.seg_taps[s];
+          for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
             if (XF) mbar_wait_acquire_cluster(&readyA[sa], pa); else mbar_wait(&readyA[sa], pa);
             tc_fence_after_sync();
-            const uint32_t a_base = smem_u32(sA + sa * kHaloBytes);
-            for (int dhi = 0; dhi < ndw; ++dhi) {
-              const int dh = (ndw == 3) ? dhi - 1 : 0;
+            const uint32_t a_base = smem_u32(sA + sa * kHaloStageBytes);
+            for (int tap = 0; tap < ntap; ++tap) {
+              const int dh = (ntap == 9) ? tap / 3 - 1 : 0;
+              const int dw = (ntap == 9) ? tap % 3 - 1 : 0;
               mbar_wait(&fullB[sb], pb);
               tc_fence_after_sync();
-              const uint64_t da = umma_desc_k_sw128(a_base + static_cast<uint32_t>((dh + 1) * kHaloW * 128));
+              // rows of the box are halo pixels at a 10-pixel pitch: tap view = row offset, SBO = one box row
+              const uint64_t da = umma_desc_k_sw128_sbo(
+                  a_base + static_cast<uint32_t>(((1 + dh) * kHaloCols + (1 + dw)) * 128), kHaloCols * 128);
               const uint64_t db = umma_desc_k_sw128(smem_u32(sB + sb * B_BYTES));
 #pragma unroll
               for (int k = 0; k < kSliceK / 16; ++k) {
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
   } else if (warp < 6) {
     // ---------------------------------------------------------------- epilogue (as conv_igemm_kernel)
     const int ew = warp & 3;
-    const int row = ew * 32 + lane;
+    const int row = ew * 32 + lane;       // = hl * 8 + wl of the 16 x 8 tile
     const bool leader = (threadIdx.x == 64);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * kHaloTileH;
-      const int w0 = (rem % p.tiles_w) * kHaloW;
+      const int w0 = (rem % p.tiles_w) * kHaloTileW;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * N);
@@ -592,8 +593,8 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
     // ---------------------------------------------------------------- transform warps (6..9)
     const int tx = threadIdx.x - 192;       // 0..127
     const int j = tx & 7;                   // logical 16-byte chunk = channels j*8 .. j*8+7 of the slice
-    const int ww = tx >> 3;                 // halo column owned by this thread (0..15)
-    const int slot = (j ^ (ww & 7)) << 4;   // physical chunk position (rows r = ww + 16*hh share r & 7)
+    const int g = tx >> 3;                  // rows r = g + 16*i  (r & 7 == g & 7 for all of them)
+    const int slot = (j ^ (g & 7)) << 4;    // physical chunk position inside the 128-byte row
     int sa = 0;
     uint32_t pa = 0;
     int cur_n = -1;
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * kHaloTileH;
-      const int w0 = (rem % p.tiles_w) * kHaloW;
+      const int w0 = (rem % p.tiles_w) * kHaloTileW;
       if (n != cur_n) {
         // (re)load this sample's GroupNorm scale/shift for every transformed segment
         named_bar_sync(3, 128);
@@ -615,11 +616,11 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
         cur_n = n;
       }
       for (int s = 0; s < p.nseg; ++s) {
-        const int ndw = (p.seg_taps[s] == 9) ? 3 : 1;
         const bool xf = p.seg_ss[s] != nullptr;
         for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
-          float sc[8], sh[8];
+          mbar_wait(&fullA[sa], pa);
           if (xf) {
+            float sc[8], sh[8];
             const float4* t4 = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(sSS) + p.seg_ss_off[s] +
                                                                ks * kSliceK + j * 8);
 #pragma unroll
@@ -627,35 +628,32 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
               const float4 q = t4[e];
               sc[2 * e] = q.x; sh[2 * e] = q.y; sc[2 * e + 1] = q.z; sh[2 * e + 1] = q.w;
             }
-          }
-          for (int di = 0; di < ndw; ++di) {
-            const int dw = (ndw == 3) ? di - 1 : 0;
-            mbar_wait(&fullA[sa], pa);
-            if (xf) {
-              uint8_t* base = sA + sa * kHaloBytes + ww * 128 + slot;
-              const bool col_ok = (w0 + dw + ww >= 0) && (w0 + dw + ww < p.W);
+            uint8_t* base = sA + sa * kHaloStageBytes + slot;
 #pragma unroll
-              for (int hh = 0; hh < kHaloRows; ++hh) {
-                uint4* ptr = reinterpret_cast<uint4*>(base + hh * (kHaloW * 128));
-                const int hy = h0 - 1 + hh;
+            for (int i = 0; i < (kHaloPix + 15) / 16; ++i) {
+              const int r = g + 16 * i;
+              if (r < kHaloPix) {
+                const int hh = r / kHaloCols, ww = r - hh * kHaloCols;
+                const int hy = h0 - 1 + hh, wx = w0 - 1 + ww;
+                uint4* ptr = reinterpret_cast<uint4*>(base + r * 128);
                 uint4 q = make_uint4(0u, 0u, 0u, 0u);
-                if (col_ok && hy >= 0 && hy < p.H) {
-                  const uint4 r = *ptr;
-                  const float2 a0 = unpack_bf16x2(r.x), a1 = unpack_bf16x2(r.y), a2 = unpack_bf16x2(r.z),
-                               a3 = unpack_bf16x2(r.w);
-                  q.x = pack_bf16x2(silu_fast(fmaf(a0.x, sc[0], sh[0])), silu_fast(fmaf(a0.y, sc[1], sh[1])));
-                  q.y = pack_bf16x2(silu_fast(fmaf(a1.x, sc[2], sh[2])), silu_fast(fmaf(a1.y, sc[3], sh[3])));
-                  q.z = pack_bf16x2(silu_fast(fmaf(a2.x, sc[4], sh[4])), silu_fast(fmaf(a2.y, sc[5], sh[5])));
-                  q.w = pack_bf16x2(silu_fast(fmaf(a3.x, sc[6], sh[6])), silu_fast(fmaf(a3.y, sc[7], sh[7])));
+                if (hy >= 0 && hy < p.H && wx >= 0 && wx < p.W) {
+                  const uint4 rr = *ptr;
+                  const float2 a0 = unpack_bf16x2(rr.x), a1 = unpack_bf16x2(rr.y), a2 = unpack_bf16x2(rr.z),
+                               a3 = unpack_bf16x2(rr.w);
+                  q.x = pack_bf16x2(silu_f(fmaf(a0.x, sc[0], sh[0])), silu_f(fmaf(a0.y, sc[1], sh[1])));
+                  q.y = pack_bf16x2(silu_f(fmaf(a1.x, sc[2], sh[2])), silu_f(fmaf(a1.y, sc[3], sh[3])));
+                  q.z = pack_bf16x2(silu_f(fmaf(a2.x, sc[4], sh[4])), silu_f(fmaf(a2.y, sc[5], sh[5])));
+                  q.w = pack_bf16x2(silu_f(fmaf(a3.x, sc[6], sh[6])), silu_f(fmaf(a3.y, sc[7], sh[7])));
                 }
                 *ptr = q;
               }
-              fence_proxy_async_smem();
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote_release_cluster(&readyA[sa], 0);
-            if (++sa == SA) { sa = 0; pa ^= 1u; }
+            fence_proxy_async_smem();
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote_release_cluster(&readyA[sa], 0);
+          if (++sa == SA) { sa = 0; pa ^= 1u; }
         }
       }
     }
@@ -845,10 +843,10 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
   {
     // "halo" kernel: 8x16 tiles, A box shared by the three vertical taps, optional fused GN+SiLU
     const bool halo_ok = !out_is_f32 && (flags & 1) && (flags & 2) && (npad == 128 || npad == 256) &&
-                         (W % kHaloW == 0) && (H % kHaloTileH == 0) &&
-                         ((static_cast<long long>(B) * (H / kHaloTileH) * (W / kHaloW)) % 2 == 0);
+                         (W % kHaloTileW == 0) && (H % kHaloTileH == 0) &&
+                         ((static_cast<long long>(B) * (H / kHaloTileH) * (W / kHaloTileW)) % 2 == 0);
     FD_REQUIRE(halo_ok || !any_xf, "fd_conv2d_igemm: fused GroupNorm+SiLU needs the halo kernel "
-               "(bf16 out, flags 3, W %% 16 == 0, H %% 8 == 0, even tile count)");
+               "(bf16 out, flags 3, W %% 8 == 0, H %% 16 == 0, even tile count)");
     if (halo_ok) {
       HaloParams hp;
       memset(&hp, 0, sizeof(hp));
@@ -865,18 +863,18 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
         if (srcs[s].scale_shift) ssoff += srcs[s].c_count;
         kb += srcs[s].c_count * srcs[s].taps;
         if (make_nhwc_map(&hp.a_map[s], srcs[s].ptr, B, H, W, srcs[s].C, srcs[s].c_begin, srcs[s].c_count,
-                          kHaloRows, kHaloW))
+                          kHaloRows, kHaloCols))
           return 1;
       }
       FD_REQUIRE(ssoff <= 512, "fd_conv2d_igemm: at most 512 transformed channels (got %d)", ssoff);
       if (make_weight_map(&hp.b_map, wpacked, npad, ktot, npad / 2)) return 1;
       FD_REQUIRE(cout == npad, "fd_conv2d_igemm: bf16 output needs cout == npad");
-      if (make_nhwc_map(&hp.out_map, out, B, H, W, cout, 0, cout, kHaloTileH, kHaloW)) return 1;
+      if (make_nhwc_map(&hp.out_map, out, B, H, W, cout, 0, cout, kHaloTileH, kHaloTileW)) return 1;
       hp.B = B;
       hp.H = H;
       hp.W = W;
       hp.tiles_h = H / kHaloTileH;
-      hp.tiles_w = W / kHaloW;
+      hp.tiles_w = W / kHaloTileW;
       hp.num_tiles = B * hp.tiles_h * hp.tiles_w;
       hp.bias = bias;
       hp.stats = stats;

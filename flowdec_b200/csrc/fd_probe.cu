@@ -1,0 +1,95 @@
+// flowdec_b200 — hardware-semantics probe (development tool, not on the product path):
+// does a K-major SWIZZLE_128B UMMA operand descriptor work when its start address is 128-byte
+// aligned but NOT 1024-byte aligned (row-shifted view into a TMA-written tile), with an arbitrary
+// stride between 8-row groups (SBO) and which `base_offset` does it need?  tools/umma_probe.py
+// compares the result with the row mapping  row(m) = row_off + (m/8)*(sbo/128) + m%8.
+#include "fd_common.cuh"
+
+namespace fd {
+
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constant__ CUtensorMap a_map,
+                                                            const __grid_constant__ CUtensorMap b_map,
+                                                            float* __restrict__ out, int row_off,
+                                                            int sbo_bytes, int base_offset) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;                 // 256 rows x 128 B
+  uint8_t* sB = smem + 256 * 128;     // 16 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 16 * 128);
+  uint64_t* done = bar + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 32);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, 256 * 128 + 16 * 128);
+    tma_load_2d(sA, &a_map, bar, 0, 0);
+    tma_load_2d(sB, &b_map, bar, 0, 0);
+    mbar_wait(bar, 0);
+    tc_fence_after_sync();
+    const uint32_t a_addr = smem_u32(sA) + static_cast<uint32_t>(row_off) * 128u;
+    uint64_t da = umma_desc_k_sw128(a_addr);
+    // replace SBO (bits 32..45) and set base_offset (bits 49..51)
+    da &= ~(static_cast<uint64_t>(0x3FFF) << 32);
+    da |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    da |= static_cast<uint64_t>(base_offset & 7) << 49;
+    const uint64_t db = umma_desc_k_sw128(smem_u32(sB));
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, k != 0);
+    umma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after_sync();
+  uint32_t v[16];
+  tmem_ld_32x32b_x16(tmem + (static_cast<uint32_t>(warp * 32) << 16), v);
+  tmem_ld_wait();
+  const int row = warp * 32 + lane;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) out[row * 16 + c] = __uint_as_float(v[c]);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace fd
+
+// a: bf16 [256][64], b: bf16 [16][64], out: fp32 [128][16]
+extern "C" int fd_umma_probe(const void* a, const void* b, float* out, int row_off, int sbo_bytes,
+                             int base_offset, cudaStream_t stream) {
+  using namespace fd;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  FD_REQUIRE(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+                 qres == cudaDriverEntryPointSuccess,
+             "cuTensorMapEncodeTiled unavailable");
+  EncodeTiledFn2 enc = reinterpret_cast<EncodeTiledFn2>(ptr);
+  CUtensorMap ma, mb;
+  cuuint64_t dimsa[2] = {64, 256}, dimsb[2] = {64, 16};
+  cuuint64_t str[1] = {128};
+  cuuint32_t boxa[2] = {64, 256}, boxb[2] = {64, 16}, es[2] = {1, 1};
+  FD_REQUIRE(enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a), dimsa, str, boxa, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, "encode a failed");
+  FD_REQUIRE(enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(b), dimsb, str, boxb, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, "encode b failed");
+  const int smem = 1024 + 256 * 128 + 16 * 128 + 64;
+  cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  umma_probe_kernel<<<1, 128, smem, stream>>>(ma, mb, out, row_off, sbo_bytes, base_offset);
+  return check_launch("fd_umma_probe");
+}

@@ -11,14 +11,14 @@ from . import _lib
 
 # CTA-pair (cta_group::2) convolution tiles; tests flip this to compare both MMA variants
 CTA_PAIRS = True
-# 8x16 "halo" tiles (A box shared by the three vertical taps; needed for fused GroupNorm+SiLU operands)
+# 16x8 "halo" tiles (one A box per k-slice serves all nine taps; needed for fused GroupNorm+SiLU operands)
 HALO_TILES = True
 
 
 def halo_eligible(B, H, W, npad):
     """mirror of the dispatch rule in fd_conv2d_igemm"""
-    return (CTA_PAIRS and HALO_TILES and npad in (128, 256) and W % 16 == 0 and H % 8 == 0
-            and (B * (H // 8) * (W // 16)) % 2 == 0)
+    return (CTA_PAIRS and HALO_TILES and npad in (128, 256) and W % 8 == 0 and H % 16 == 0
+            and (B * (H // 16) * (W // 8)) % 2 == 0)
 
 # when set to a list, conv_igemm appends (start_event, end_event, algorithmic_flops) per launch
 # (bench.py's roofline leg; events are recorded on the launching stream)

@@ -55,9 +55,9 @@ struct fd_conv_src {
  * [B, S, cout, 2] with S = 4 * H*W/128 slabs (one per epilogue warp and tile), consumed by
  * fd_gn_finalize — the statistics pass of the next GroupNorm fused into this conv's epilogue.
  * max_ctas: 0 = one persistent CTA per SM.  flags bit 0: CTA pairs (cta_group::2, 256-row MMAs, weight
- * tile split across the pair) when the tile count is even; bit 1: 8x16-pixel "halo" tiles (one A box per
- * (dw, k-slice) shared by the three vertical taps) when W % 16 == 0 and H % 8 == 0 — required for
- * sources with scale_shift != NULL (GroupNorm+SiLU fused into the operand path). */
+ * tile split across the pair) when the tile count is even; bit 1: 16x8-pixel "halo" tiles (ONE 18x10-pixel
+ * A box per k-slice serves all nine taps through row-shifted swizzled descriptors) when W % 8 == 0 and
+ * H % 16 == 0 — required for sources with scale_shift != NULL (GroupNorm+SiLU fused into the operand). */
 int fd_conv2d_igemm(const struct fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot,
                     const float* bias, void* out, int out_is_f32, int cout, int npad, int B, int H,
                     int W, float* stats, int max_ctas, int flags, fd_stream_t stream);

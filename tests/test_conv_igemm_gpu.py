@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True, params=[(True, True), (True, False), (False, False)],
                 ids=["halo_pair", "cta_pair", "single_cta"])
 def _mma_variant(request):
-    """every conv test runs with 8x16 halo tiles (CTA pairs), plain CTA pairs and single-CTA MMAs"""
+    """every conv test runs with 16x8 halo tiles (CTA pairs), plain CTA pairs and single-CTA MMAs"""
     from flowdec_b200 import ops
     old = (ops.CTA_PAIRS, ops.HALO_TILES)
     ops.CTA_PAIRS, ops.HALO_TILES = request.param
@@ -157,8 +157,8 @@ def test_pyramid_conv_gemm_first_shift_after():
     assert (out2 - ref2).abs().max().item() <= 1e-4 * ref2.abs().max().item() + 1e-4
 
 
-@pytest.mark.parametrize("B,H,W,C1,C2,Cout", [(1, 16, 16, 64, 0, 256), (2, 32, 48, 256, 0, 256), (2, 24, 32, 256, 64, 256),
-                                              (1, 96, 32, 128, 256, 128), (3, 8, 64, 256, 256, 256)])
+@pytest.mark.parametrize("B,H,W,C1,C2,Cout", [(1, 16, 16, 64, 0, 256), (2, 32, 48, 256, 0, 256), (2, 48, 8, 256, 64, 256),
+                                              (1, 96, 32, 128, 256, 128), (3, 16, 64, 256, 256, 256)])
 def test_conv_fused_groupnorm_silu_operand(B, H, W, C1, C2, Cout):
     """halo kernel with scale_shift: conv(SiLU(x*scale+shift)) incl. zero padding of the ACTIVATED
     tensor, over a virtual concat of two raw sources, plus a raw 1x1 skip segment."""
