@@ -182,7 +182,7 @@ class NCSNpp(nn.Module):
         self.stats_slabs = 64
         self.fuse_stats = True     # GroupNorm partial sums produced by the conv epilogue
         self.pyramid_shift_after_gemm = True
-        self.fuse_gn_into_conv = True   # GroupNorm+SiLU applied inside the conv kernel (halo tiles)
+        self.fuse_gn_into_conv = True   # GroupNorm+SiLU applied inside the conv kernel (needs ops.HALO_TILES)
         self.max_ctas = 0
 
     # ------------------------------------------------------------------ parameter management

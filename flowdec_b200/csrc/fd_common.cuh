@@ -97,6 +97,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// non-blocking probe (mbarrier.test_wait never suspends the thread, unlike try_wait)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // Spin on the barrier phase.  A pipeline bug would otherwise hang the GPU until the
 // driver's watchdog; after ~4 s of polling we trap so the launch fails loudly instead.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -26,6 +26,7 @@
 #include "fd_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace fd {
@@ -388,6 +389,7 @@ struct HaloParams {
   int tiles_h, tiles_w, num_tiles;
   const float* bias;
   float* stats;
+  long long* dbg;                // optional [16] cycle counters written by block 0 (tools/halo_dbg.py)
 };
 
 template <int N>
@@ -460,28 +462,45 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer (A halo + B rings)
+    // One thread feeds both rings.  B tiles are issued in consumption order (blocking on emptyB);
+    // A boxes are issued AHEAD of that order whenever a slot is free (non-blocking test_wait), so the
+    // latency of an A box (and of its in-smem transform) is not tied to the depth of the B ring.
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
-        const int n = tile / tiles_per_img;
-        const int rem = tile - n * tiles_per_img;
+      int a_tile = tile_first, a_s = 0, a_ks = 0;   // next A stage to issue
+      int a_ahead = 0;                               // A stages issued whose B tiles have not been started
+      auto issue_A = [&]() {
+        const int n = a_tile / tiles_per_img;
+        const int rem = a_tile - n * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * kHaloTileH;
         const int w0 = (rem % p.tiles_w) * kHaloTileW;
+        if (XF) {
+          mbar_expect_tx(&fullA[sa], kHaloTxBytes);
+          tma_load_4d(sA + sa * kHaloStageBytes, &p.a_map[a_s], &fullA[sa], a_ks * kSliceK, w0 - 1, h0 - 1, n);
+        } else {
+          if (leader_cta) mbar_expect_tx(&readyA[sa], 2 * kHaloTxBytes);
+          else mbar_arrive_remote(&readyA[sa], 0);
+          tma_load_4d_2sm(sA + sa * kHaloStageBytes, &p.a_map[a_s], &readyA[sa], a_ks * kSliceK, w0 - 1, h0 - 1, n);
+        }
+        if (++sa == SA) { sa = 0; pa ^= 1u; }
+        if (++a_ks == p.seg_kslices[a_s]) {
+          a_ks = 0;
+          if (++a_s == p.nseg) { a_s = 0; a_tile += tile_stride; }
+        }
+        ++a_ahead;
+      };
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
         for (int s = 0; s < p.nseg; ++s) {
           const int ntap = p.seg_taps[s];
           for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
-            mbar_wait(&emptyA[sa], pa ^ 1u);
-            if (XF) {
-              mbar_expect_tx(&fullA[sa], kHaloTxBytes);
-              tma_load_4d(sA + sa * kHaloStageBytes, &p.a_map[s], &fullA[sa], ks * kSliceK, w0 - 1, h0 - 1, n);
-            } else {
-              if (leader_cta) mbar_expect_tx(&readyA[sa], 2 * kHaloTxBytes);
-              else mbar_arrive_remote(&readyA[sa], 0);
-              tma_load_4d_2sm(sA + sa * kHaloStageBytes, &p.a_map[s], &readyA[sa], ks * kSliceK, w0 - 1, h0 - 1, n);
+            if (a_ahead == 0) {            // this stage's own A box: must go out now
+              mbar_wait(&emptyA[sa], pa ^ 1u);
+              issue_A();
             }
-            if (++sa == SA) { sa = 0; pa ^= 1u; }
+            --a_ahead;
             for (int tap = 0; tap < ntap; ++tap) {
+              while (a_tile < p.num_tiles && a_ahead < SA && mbar_test_wait(&emptyA[sa], pa ^ 1u)) issue_A();
               const int kcol = p.seg_kbase[s] + tap * p.seg_cin[s] + ks * kSliceK;
               mbar_wait(&emptyB[sb], pb ^ 1u);
               if (leader_cta) mbar_expect_tx(&fullB[sb], 2 * B_BYTES);
@@ -501,22 +520,30 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
       uint32_t pa = 0, pb = 0;
       int acc = 0, issued = 0;
       uint32_t acc_phase = 0;
+      long long w_tempty = 0, w_ready = 0, w_fullb = 0, tq = 0;
+      const long long t_begin = p.dbg ? clock64() : 0;
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
         ++issued;
+        if (p.dbg) tq = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        if (p.dbg) w_tempty += clock64() - tq;
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * N);
         uint32_t first = 1;
         for (int s = 0; s < p.nseg; ++s) {
           const int ntap = p.seg_taps[s];
           for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
+            if (p.dbg) tq = clock64();
             if (XF) mbar_wait_acquire_cluster(&readyA[sa], pa); else mbar_wait(&readyA[sa], pa);
+            if (p.dbg) w_ready += clock64() - tq;
             tc_fence_after_sync();
             const uint32_t a_base = smem_u32(sA + sa * kHaloStageBytes);
             for (int tap = 0; tap < ntap; ++tap) {
               const int dh = (ntap == 9) ? tap / 3 - 1 : 0;
               const int dw = (ntap == 9) ? tap % 3 - 1 : 0;
+              if (p.dbg) tq = clock64();
               mbar_wait(&fullB[sb], pb);
+              if (p.dbg) w_fullb += clock64() - tq;
               tc_fence_after_sync();
               // rows of the box are halo pixels at a 10-pixel pitch: tap view = row offset, SBO = one box row
               const uint64_t da = umma_desc_k_sw128_sbo(
@@ -542,6 +569,13 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
       if (issued > 0)
         for (int j = (issued >= 2 ? issued - 2 : issued - 1); j < issued; ++j)
           mbar_wait(&tempty_bar[j & 1], static_cast<uint32_t>((j >> 1) & 1));
+      if (p.dbg != nullptr && blockIdx.x == 0) {
+        p.dbg[0] = clock64() - t_begin;
+        p.dbg[1] = w_tempty;
+        p.dbg[2] = w_ready;
+        p.dbg[3] = w_fullb;
+        p.dbg[4] = issued;
+      }
     }
   } else if (warp < 6) {
     // ---------------------------------------------------------------- epilogue (as conv_igemm_kernel)
@@ -878,6 +912,10 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
       hp.num_tiles = B * hp.tiles_h * hp.tiles_w;
       hp.bias = bias;
       hp.stats = stats;
+      {
+        const char* e = getenv("FD_HALO_DBG");   // device pointer (decimal) of an int64[16] buffer
+        hp.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr;
+      }
       if (npad == 256) return any_xf ? launch_halo<256, true>(hp, max_ctas, stream)
                                      : launch_halo<256, false>(hp, max_ctas, stream);
       return any_xf ? launch_halo<128, true>(hp, max_ctas, stream) : launch_halo<128, false>(hp, max_ctas, stream);

@@ -62,6 +62,55 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constan
   if (warp == 0) tmem_dealloc(tmem, 32);
 }
 
+// throughput probe: `iters` back-to-back M=128 x N=256 x K=16 MMAs whose A descriptor starts at row
+// `row_off` of a 256-row tile with 8-row-group stride `sbo_bytes`; reports cycles per MMA.
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(const __grid_constant__ CUtensorMap a_map,
+                                                           const __grid_constant__ CUtensorMap b_map,
+                                                           long long* __restrict__ cycles, int row_off,
+                                                           int sbo_bytes, int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;                  // 256 rows x 128 B
+  uint8_t* sB = smem + 256 * 128;      // 256 rows x 128 B (N = 256)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 256 * 128);
+  uint64_t* done = bar + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, 2 * 256 * 128);
+    tma_load_2d(sA, &a_map, bar, 0, 0);
+    tma_load_2d(sB, &b_map, bar, 0, 0);
+    mbar_wait(bar, 0);
+    tc_fence_after_sync();
+    const uint64_t da = umma_desc_k_sw128_sbo(smem_u32(sA) + static_cast<uint32_t>(row_off) * 128u,
+                                              static_cast<uint32_t>(sbo_bytes));
+    const uint64_t db = umma_desc_k_sw128(smem_u32(sB));
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i)
+      umma_bf16(tmem, da + static_cast<uint64_t>((i & 3) * 2), db + static_cast<uint64_t>((i & 3) * 2), idesc, i != 0);
+    umma_commit(done);
+    mbar_wait(done, 0);
+    const long long t1 = clock64();
+    cycles[0] = t1 - t0;
+  }
+  __syncthreads();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -92,4 +141,30 @@ extern "C" int fd_umma_probe(const void* a, const void* b, float* out, int row_o
   cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   umma_probe_kernel<<<1, 128, smem, stream>>>(ma, mb, out, row_off, sbo_bytes, base_offset);
   return check_launch("fd_umma_probe");
+}
+
+// a: bf16 [256][64], b: bf16 [256][64]; cycles: device int64[1]
+extern "C" int fd_umma_rate(const void* a, const void* b, long long* cycles, int row_off, int sbo_bytes,
+                            int iters, cudaStream_t stream) {
+  using namespace fd;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  FD_REQUIRE(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+                 qres == cudaDriverEntryPointSuccess,
+             "cuTensorMapEncodeTiled unavailable");
+  EncodeTiledFn2 enc = reinterpret_cast<EncodeTiledFn2>(ptr);
+  CUtensorMap ma, mb;
+  cuuint64_t dims[2] = {64, 256};
+  cuuint64_t str[1] = {128};
+  cuuint32_t box[2] = {64, 256}, es[2] = {1, 1};
+  FD_REQUIRE(enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a), dims, str, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, "encode a failed");
+  FD_REQUIRE(enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(b), dims, str, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, "encode b failed");
+  const int smem = 1024 + 2 * 256 * 128 + 64;
+  cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  umma_rate_kernel<<<1, 128, smem, stream>>>(ma, mb, cycles, row_off, sbo_bytes, iters);
+  return check_launch("fd_umma_rate");
 }

@@ -50,6 +50,24 @@ def test_backbone_forward_vs_golden_and_oracle(model):
     assert torch.equal(torch.view_as_real(v2.cpu()), v)
 
 
+def test_backbone_with_fused_groupnorm_halo_kernel(model):
+    """experimental path: 16x8 halo tiles with GroupNorm+SiLU applied inside the conv kernel
+    (ops.HALO_TILES) must meet the same parity bar as the default path"""
+    from flowdec_b200 import ops
+    I = golden_inputs()
+    gold = torch.from_numpy(np.load(GOLD)["backbone_v"])
+    old = ops.HALO_TILES
+    ops.HALO_TILES = True
+    try:
+        with torch.no_grad():
+            v = model.backbone(I["X"].cuda(), I["Y"].cuda(), I["t"].cuda())
+    finally:
+        ops.HALO_TILES = old
+    r = rel_l2(torch.view_as_real(v.cpu()), gold)
+    print(f"\nbackbone (halo tiles + fused GroupNorm/SiLU) rel-L2 vs reference golden: {r:.4e}")
+    assert r <= 3e-2
+
+
 @pytest.mark.parametrize("N,solver", [(1, "euler"), (1, "midpoint"), (2, "heun2_eulerlast")])
 def test_enhance_vs_golden(model, N, solver):
     I = golden_inputs()
