@@ -72,6 +72,7 @@ class FlowModel(EnhancementModel):
         self._graphs = {}
         self.use_cuda_graph = True
         self.max_batch = 8          # clips per backbone pass (micro-batch)
+        self.max_frames_per_pass = 4096   # padded STFT frames per backbone pass (8 clips x 4 s)
         self.overlap_streams = 2    # micro-batches in flight on separate CUDA streams
         self._streams = []
         self._sig_cache = None
@@ -91,6 +92,12 @@ class FlowModel(EnhancementModel):
         if torch.is_tensor(t) and t.ndim == 0:
             t = t.unsqueeze(0)
         return self.backbone(xt, y, t)
+
+    def _micro_batch(self, Tp):
+        """clips per backbone pass: bounded by `max_batch` and by `max_frames_per_pass` STFT frames, so
+        that long clips (the reference CLI accepts up to 30 s, enhance.py:115) keep the activation
+        workspace at the size it has for 8 x 4 s"""
+        return max(1, min(self.max_batch, self.max_frames_per_pass // max(Tp, 1)))
 
     def _side_streams(self, n):
         while len(self._streams) < n:
@@ -131,7 +138,8 @@ class FlowModel(EnhancementModel):
             for (te, src, dst, b1, c1, b2, c2, coef) in stages(solver, t, dt):
                 # micro-batches are independent: alternate them over `overlap_streams` CUDA streams so
                 # the HBM-bound GroupNorm/FIR passes of one overlap the tensor-bound convs of another
-                chunks = [(lo, min(B, lo + self.max_batch)) for lo in range(0, B, self.max_batch)]
+                mb = self._micro_batch(Tp)
+                chunks = [(lo, min(B, lo + mb)) for lo in range(0, B, mb)]
                 nlanes = max(1, min(self.overlap_streams, len(chunks)))
                 main = torch.cuda.current_stream()
                 lanes = [main] + self._side_streams(nlanes - 1)
@@ -296,9 +304,11 @@ class ScoreModel(EnhancementModel):
                 z = torch.randn(B * C, 768, Tp, dtype=torch.complex64, device=dev)
             return torch.view_as_real(z).contiguous()
 
+        mb = max(1, min(self.max_batch, 4096 // Tp))
+
         def backbone_stage(x, t, out, c1, c2, base3, c3, coef):
-            for lo in range(0, B * C, self.max_batch):
-                hi = min(B * C, lo + self.max_batch)
+            for lo in range(0, B * C, mb):
+                hi = min(B * C, lo + mb)
                 bb.velocity(x[lo:hi], Y[lo:hi], float(t), out=out[lo:hi], base1=x[lo:hi], c1=c1,
                             base2=Y[lo:hi], c2=c2, base3=base3[lo:hi] if base3 is not None else None,
                             c3=c3, coef=coef)

@@ -132,3 +132,18 @@ def test_batch_independence_and_microbatching(model):
     one = model.enhance(y[1:2], N=1, solver="midpoint", noise=eps[1:2])
     assert torch.equal(full, split)
     assert torch.equal(full[1:2], one)
+
+
+def test_long_and_ragged_clips(model):
+    """a 12.3 s clip (Tp = 1536 frames, forces micro-batch 2) and a length that is not a hop multiple:
+    finite output of the right shape, and the per-clip result does not depend on its batch neighbours"""
+    from flowdec_b200.util.synth import synth_waveforms
+    L = 590_411
+    y = synth_waveforms(3, L, seed=77, kind="gauss")
+    g = torch.Generator().manual_seed(3)
+    Tp = 64 * -(-(1 + L // 384) // 64)
+    eps = torch.randn(3, 1, 768, Tp, dtype=torch.complex64, generator=g)
+    out = model.enhance(y, N=1, solver="euler", noise=eps)
+    assert out.shape == y.shape and torch.isfinite(out).all()
+    one = model.enhance(y[2:3], N=1, solver="euler", noise=eps[2:3])
+    assert torch.equal(one, out[2:3])
