@@ -42,6 +42,32 @@ __device__ __forceinline__ float silu_f(float v) {
   return __fdividef(v, 1.0f + __expf(-v));
 }
 
+// same, straight-line (no denormal range fix-ups): x * rcp(1 + 2^(-x log2 e)); 5 instructions
+__device__ __forceinline__ float silu_lean(float v) {
+  float e, r;
+  const float t = v * -1.4426950408889634f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  const float d = 1.0f + e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return v * r;
+}
+
+// explicit shared-window accesses: pointers carved out of the dynamic smem buffer by integer
+// alignment lose their address space, and the compiler falls back to generic LD/ST (slower)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 // SiLU via one MUFU op: x * sigmoid(x) = 0.5 x (1 + tanh(x/2)); tanh.approx.f32 has 2^-11 relative
 // error, i.e. |error| <= 2.5e-4 |x| -- an order of magnitude below the bf16 rounding that follows.
 // Used by the FIR-resampling variants, which evaluate several activations per output.
@@ -400,6 +426,19 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
       : "memory");
+}
+
+// one lane of a converged warp (all 32 lanes must execute this)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

@@ -73,11 +73,17 @@ struct ConvCfg {
 // GroupNorm partial sums of the 32 columns over the warp's 32 rows.  The column reduction is a
 // transpose-reduce butterfly (31 shuffles per statistic instead of 32*5): after the xor-16 step
 // every lane keeps 16 columns, ... after xor-1 lane L holds the total of column L.
-__device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], const float* bs, uint8_t* rowp,
+__device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], uint32_t bs_addr, uint32_t rowp_addr,
                                               int row, int j0, float* stat_dst, int lane) {
   float f[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + bs[i];
+  for (int i = 0; i < 8; ++i) {
+    const float4 b4 = lds_f4(bs_addr + i * 16);      // bias (warp-wide broadcast read)
+    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
+    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint4 q;
@@ -85,7 +91,7 @@ __device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], const flo
     q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
     q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
     q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-    *reinterpret_cast<uint4*>(rowp + (((j0 + j) ^ (row & 7)) << 4)) = q;
+    sts128(rowp_addr + static_cast<uint32_t>(((j0 + j) ^ (row & 7)) << 4), q);
   }
   if (stat_dst != nullptr) {
     float q[32];
@@ -219,7 +225,10 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0 && leader_cta) {
+    // The whole warp walks the loop (warp-uniform control flow and operands, so descriptors live in
+    // uniform registers and every tcgen05.mma is issued without a per-thread -> uniform register
+    // round trip); one elected lane issues the MMAs and commits.
+    if (leader_cta) {
       constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * kTileM : kTileM, N);
       int stage = 0;
       uint32_t phase = 0;
@@ -236,23 +245,28 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           tc_fence_after_sync();
           const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * kABytes));
           const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * B_BYTES));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kSliceK / 16; ++k) {
-            // +32 bytes per K=16 step inside the 128-byte swizzle span (encoded >>4)
-            if (CTA2)
-              umma_bf16_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                            idesc, static_cast<uint32_t>((ki | k) != 0));
-            else
-              umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                        idesc, static_cast<uint32_t>((ki | k) != 0));
+            for (int k = 0; k < kSliceK / 16; ++k) {
+              // +32 bytes per K=16 step inside the 128-byte swizzle span (encoded >>4)
+              if (CTA2)
+                umma_bf16_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                              idesc, static_cast<uint32_t>((ki | k) != 0));
+              else
+                umma_bf16(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                          idesc, static_cast<uint32_t>((ki | k) != 0));
+            }
+            if (CTA2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+            if (ki == k_iters - 1) {
+              if (CTA2) umma_commit_2sm(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+            }
           }
-          if (CTA2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if (CTA2) umma_commit_2sm(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -324,10 +338,10 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           // the TMA store that last read this staging tile must have drained it
           if (leader) tma_store_wait_read<1>();
           named_bar_sync(1, 128);
-          const float* bs = sBias + ch * 64;
-          uint8_t* rowp = stg + row * 128;
+          const uint32_t bs = smem_u32(sBias + ch * 64);
+          const uint32_t rowp = smem_u32(stg + row * 128);
           epilogue_half(v0, bs, rowp, row, 0, stat_row ? stat_row + (ch * 64) * 2 : nullptr, lane);
-          epilogue_half(v1, bs + 32, rowp, row, 4, stat_row ? stat_row + (ch * 64 + 32) * 2 : nullptr, lane);
+          epilogue_half(v1, bs + 128, rowp, row, 4, stat_row ? stat_row + (ch * 64 + 32) * 2 : nullptr, lane);
           fence_proxy_async_smem();
           named_bar_sync(2, 128);
           if (leader) {
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
 //   separate GroupNorm+SiLU pass and its bf16 round trip through HBM (layerspp.py:253,274 fused into
 //   the operand path of Conv_0 / Conv_1).
 //   Weights: a separate ring of [N/2 x 64] tiles, one per (tap, k-slice).
-// warps: 0 producer (A and B rings), 1 MMA issuer (leader CTA), 2-5 epilogue, 6-9 transform.
+// warps: 0 A producer, 1 MMA issuer (leader CTA), 2-5 epilogue, 6 weight producer, 7-14 transform.
 // =================================================================================
 constexpr int kHaloRows = 18;
 constexpr int kHaloCols = 10;
@@ -405,7 +419,7 @@ struct HaloCfg {
 };
 
 template <int N, bool XF>
-__global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(XF ? 480 : 224, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   using Cfg = HaloCfg<N>;
   constexpr int SA = Cfg::kStagesA, SB = Cfg::kStagesB, B_BYTES = Cfg::kBBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -435,7 +449,7 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) {
       mbar_init(&fullA[s], 1);
-      mbar_init(&readyA[s], XF ? 8 : 2);   // XF: 4 transform warps of each CTA; else expect_tx + peer arrive
+      mbar_init(&readyA[s], XF ? 16 : 2);  // XF: 8 transform warps of each CTA; else expect_tx + peer arrive
       mbar_init(&emptyA[s], 1);
     }
     for (int s = 0; s < SB; ++s) {
@@ -461,46 +475,43 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
   const int tiles_per_img = p.tiles_h * p.tiles_w;
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- producer (A halo + B rings)
-    // One thread feeds both rings.  B tiles are issued in consumption order (blocking on emptyB);
-    // A boxes are issued AHEAD of that order whenever a slot is free (non-blocking test_wait), so the
-    // latency of an A box (and of its in-smem transform) is not tied to the depth of the B ring.
+    // ---------------------------------------------------------------- A producer (halo boxes)
+    // (the weight ring has its own producer thread in warp 6, so neither ring's latency is
+    //  coupled to the other's depth)
     if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      int a_tile = tile_first, a_s = 0, a_ks = 0;   // next A stage to issue
-      int a_ahead = 0;                               // A stages issued whose B tiles have not been started
-      auto issue_A = [&]() {
-        const int n = a_tile / tiles_per_img;
-        const int rem = a_tile - n * tiles_per_img;
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
+        const int n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * kHaloTileH;
         const int w0 = (rem % p.tiles_w) * kHaloTileW;
-        if (XF) {
-          mbar_expect_tx(&fullA[sa], kHaloTxBytes);
-          tma_load_4d(sA + sa * kHaloStageBytes, &p.a_map[a_s], &fullA[sa], a_ks * kSliceK, w0 - 1, h0 - 1, n);
-        } else {
-          if (leader_cta) mbar_expect_tx(&readyA[sa], 2 * kHaloTxBytes);
-          else mbar_arrive_remote(&readyA[sa], 0);
-          tma_load_4d_2sm(sA + sa * kHaloStageBytes, &p.a_map[a_s], &readyA[sa], a_ks * kSliceK, w0 - 1, h0 - 1, n);
+        for (int s = 0; s < p.nseg; ++s) {
+          for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
+            mbar_wait(&emptyA[sa], pa ^ 1u);
+            if (XF) {
+              mbar_expect_tx(&fullA[sa], kHaloTxBytes);
+              tma_load_4d(sA + sa * kHaloStageBytes, &p.a_map[s], &fullA[sa], ks * kSliceK, w0 - 1, h0 - 1, n);
+            } else {
+              if (leader_cta) mbar_expect_tx(&readyA[sa], 2 * kHaloTxBytes);
+              else mbar_arrive_remote(&readyA[sa], 0);
+              tma_load_4d_2sm(sA + sa * kHaloStageBytes, &p.a_map[s], &readyA[sa], ks * kSliceK, w0 - 1, h0 - 1, n);
+            }
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
+          }
         }
-        if (++sa == SA) { sa = 0; pa ^= 1u; }
-        if (++a_ks == p.seg_kslices[a_s]) {
-          a_ks = 0;
-          if (++a_s == p.nseg) { a_s = 0; a_tile += tile_stride; }
-        }
-        ++a_ahead;
-      };
+      }
+    }
+  } else if (warp == 6) {
+    // ---------------------------------------------------------------- B producer (weight tiles)
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
         for (int s = 0; s < p.nseg; ++s) {
           const int ntap = p.seg_taps[s];
           for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
-            if (a_ahead == 0) {            // this stage's own A box: must go out now
-              mbar_wait(&emptyA[sa], pa ^ 1u);
-              issue_A();
-            }
-            --a_ahead;
             for (int tap = 0; tap < ntap; ++tap) {
-              while (a_tile < p.num_tiles && a_ahead < SA && mbar_test_wait(&emptyA[sa], pa ^ 1u)) issue_A();
               const int kcol = p.seg_kbase[s] + tap * p.seg_cin[s] + ks * kSliceK;
               mbar_wait(&emptyB[sb], pb ^ 1u);
               if (leader_cta) mbar_expect_tx(&fullB[sb], 2 * B_BYTES);
@@ -514,7 +525,8 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer (leader CTA)
-    if (lane == 0 && leader_cta) {
+    // warp-uniform loop, one elected lane issues (descriptors stay in uniform registers)
+    if (leader_cta) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * kTileM, N);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -532,12 +544,14 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
         uint32_t first = 1;
         for (int s = 0; s < p.nseg; ++s) {
           const int ntap = p.seg_taps[s];
+          const bool last_seg = (s == p.nseg - 1);
           for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
             if (p.dbg) tq = clock64();
             if (XF) mbar_wait_acquire_cluster(&readyA[sa], pa); else mbar_wait(&readyA[sa], pa);
             if (p.dbg) w_ready += clock64() - tq;
             tc_fence_after_sync();
             const uint32_t a_base = smem_u32(sA + sa * kHaloStageBytes);
+            const bool last_stage = last_seg && (ks == p.seg_kslices[s] - 1);
             for (int tap = 0; tap < ntap; ++tap) {
               const int dh = (ntap == 9) ? tap / 3 - 1 : 0;
               const int dw = (ntap == 9) ? tap % 3 - 1 : 0;
@@ -549,27 +563,31 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
               const uint64_t da = umma_desc_k_sw128_sbo(
                   a_base + static_cast<uint32_t>(((1 + dh) * kHaloCols + (1 + dw)) * 128), kHaloCols * 128);
               const uint64_t db = umma_desc_k_sw128(smem_u32(sB + sb * B_BYTES));
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < kSliceK / 16; ++k) {
-                umma_bf16_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                              idesc, first ? 0u : 1u);
-                first = 0;
+                for (int k = 0; k < kSliceK / 16; ++k)
+                  umma_bf16_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                                idesc, (first && k == 0) ? 0u : 1u);
+                umma_commit_2sm(&emptyB[sb]);
+                if (tap == ntap - 1) {
+                  umma_commit_2sm(&emptyA[sa]);
+                  if (last_stage) umma_commit_2sm(&tfull_bar[acc]);
+                }
               }
-              umma_commit_2sm(&emptyB[sb]);
+              __syncwarp();
+              first = 0;
               if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
-            umma_commit_2sm(&emptyA[sa]);
             if (++sa == SA) { sa = 0; pa ^= 1u; }
           }
         }
-        umma_commit_2sm(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
       if (issued > 0)
         for (int j = (issued >= 2 ? issued - 2 : issued - 1); j < issued; ++j)
           mbar_wait(&tempty_bar[j & 1], static_cast<uint32_t>((j >> 1) & 1));
-      if (p.dbg != nullptr && blockIdx.x == 0) {
+      if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
         p.dbg[0] = clock64() - t_begin;
         p.dbg[1] = w_tempty;
         p.dbg[2] = w_ready;
@@ -597,21 +615,25 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
       float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * (tiles_per_img * 4) + slab) * N) * 2 : nullptr;
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ++ch) {
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32b_x32(t_row + ch * 64, v0);
-        tmem_ld_32x32b_x32(t_row + ch * 64 + 32, v1);
-        tmem_ld_wait();
-        if (ch == kChunks - 1) {
-          tc_fence_before_sync();
-          mbar_arrive_remote(&tempty_bar[acc], 0);
-        }
         uint8_t* stg = sOut + (ch & 1) * (kTileM * 128);
         if (leader) tma_store_wait_read<1>();
         named_bar_sync(1, 128);
-        const float* bs = sBias + ch * 64;
-        uint8_t* rowp = stg + row * 128;
-        epilogue_half(v0, bs, rowp, row, 0, stat_row ? stat_row + (ch * 64) * 2 : nullptr, lane);
-        epilogue_half(v1, bs + 32, rowp, row, 4, stat_row ? stat_row + (ch * 64 + 32) * 2 : nullptr, lane);
+        const uint32_t bs = smem_u32(sBias + ch * 64);
+        const uint32_t rowp = smem_u32(stg + row * 128);
+        {
+          // one 32-column half at a time: keeps the register footprint low enough for 480 threads
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + ch * 64, v);
+          tmem_ld_wait();
+          epilogue_half(v, bs, rowp, row, 0, stat_row ? stat_row + (ch * 64) * 2 : nullptr, lane);
+          tmem_ld_32x32b_x32(t_row + ch * 64 + 32, v);
+          tmem_ld_wait();
+          if (ch == kChunks - 1) {
+            tc_fence_before_sync();
+            mbar_arrive_remote(&tempty_bar[acc], 0);
+          }
+          epilogue_half(v, bs + 128, rowp, row, 4, stat_row ? stat_row + (ch * 64 + 32) * 2 : nullptr, lane);
+        }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (leader) {
@@ -623,15 +645,16 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
       if (acc == 0) acc_phase ^= 1u;
     }
     if (leader) tma_store_wait_all<0>();
-  } else if (XF) {
-    // ---------------------------------------------------------------- transform warps (6..9)
-    const int tx = threadIdx.x - 192;       // 0..127
+  } else if (XF && warp >= 7) {
+    // ---------------------------------------------------------------- transform warps (7..14)
+    const int tx = threadIdx.x - 224;       // 0..255
     const int j = tx & 7;                   // logical 16-byte chunk = channels j*8 .. j*8+7 of the slice
-    const int g = tx >> 3;                  // rows r = g + 16*i  (r & 7 == g & 7 for all of them)
+    const int g = tx >> 3;                  // rows r = g + 32*i  (r & 7 == g & 7 for all of them)
     const int slot = (j ^ (g & 7)) << 4;    // physical chunk position inside the 128-byte row
     int sa = 0;
     uint32_t pa = 0;
     int cur_n = -1;
+    long long x_wait = 0, x_work = 0, xq = 0, x_fence = 0, x_ld = 0;
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
       const int n = tile / tiles_per_img;
       const int rem = tile - n * tiles_per_img;
@@ -639,57 +662,79 @@ __global__ void __launch_bounds__(XF ? 320 : 192, 1) conv_halo_kernel(const __gr
       const int w0 = (rem % p.tiles_w) * kHaloTileW;
       if (n != cur_n) {
         // (re)load this sample's GroupNorm scale/shift for every transformed segment
-        named_bar_sync(3, 128);
+        named_bar_sync(3, 256);
         for (int s = 0; s < p.nseg; ++s) {
           if (p.seg_ss[s] == nullptr) continue;
           const float2* src = reinterpret_cast<const float2*>(p.seg_ss[s]) + static_cast<size_t>(n) * p.seg_ss_pitch[s];
           float2* dst = reinterpret_cast<float2*>(sSS) + p.seg_ss_off[s];
-          for (int c = tx; c < p.seg_cin[s]; c += 128) dst[c] = src[c];
+          for (int c = tx; c < p.seg_cin[s]; c += 256) dst[c] = src[c];
         }
-        named_bar_sync(3, 128);
+        named_bar_sync(3, 256);
         cur_n = n;
       }
       for (int s = 0; s < p.nseg; ++s) {
         const bool xf = p.seg_ss[s] != nullptr;
         for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
+          if (p.dbg) xq = clock64();
           mbar_wait(&fullA[sa], pa);
+          if (p.dbg) { const long long now = clock64(); x_wait += now - xq; xq = now; }
           if (xf) {
             float sc[8], sh[8];
-            const float4* t4 = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(sSS) + p.seg_ss_off[s] +
-                                                               ks * kSliceK + j * 8);
+            const uint32_t ss_addr = smem_u32(sSS) + static_cast<uint32_t>(p.seg_ss_off[s] + ks * kSliceK + j * 8) * 8u;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float4 q = t4[e];
+              const float4 q = lds_f4(ss_addr + e * 16);
               sc[2 * e] = q.x; sh[2 * e] = q.y; sc[2 * e + 1] = q.z; sh[2 * e + 1] = q.w;
             }
-            uint8_t* base = sA + sa * kHaloStageBytes + slot;
+            const uint32_t base = smem_u32(sA + sa * kHaloStageBytes) + static_cast<uint32_t>(slot);
+            constexpr int kItems = (kHaloPix + 31) / 32;     // 6 rows per thread (the last one partial)
+            // phase 1: issue every load (independent -> the LSU pipelines them)
+            uint4 raw[kItems];
+            bool ok[kItems];
 #pragma unroll
-            for (int i = 0; i < (kHaloPix + 15) / 16; ++i) {
-              const int r = g + 16 * i;
+            for (int i = 0; i < kItems; ++i) {
+              const int r = g + 32 * i;
+              const int hh = r / kHaloCols, ww = r - hh * kHaloCols;
+              const int hy = h0 - 1 + hh, wx = w0 - 1 + ww;
+              ok[i] = (r < kHaloPix) && hy >= 0 && hy < p.H && wx >= 0 && wx < p.W;
+              raw[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (ok[i]) raw[i] = lds128(base + static_cast<uint32_t>(r) * 128u);
+            }
+            if (p.dbg) { const long long now = clock64(); x_ld += now - xq; }
+            // phase 2: affine + SiLU (one MUFU op per element) and store back; out-of-image rows -> 0
+#pragma unroll
+            for (int i = 0; i < kItems; ++i) {
+              const int r = g + 32 * i;
               if (r < kHaloPix) {
-                const int hh = r / kHaloCols, ww = r - hh * kHaloCols;
-                const int hy = h0 - 1 + hh, wx = w0 - 1 + ww;
-                uint4* ptr = reinterpret_cast<uint4*>(base + r * 128);
                 uint4 q = make_uint4(0u, 0u, 0u, 0u);
-                if (hy >= 0 && hy < p.H && wx >= 0 && wx < p.W) {
-                  const uint4 rr = *ptr;
-                  const float2 a0 = unpack_bf16x2(rr.x), a1 = unpack_bf16x2(rr.y), a2 = unpack_bf16x2(rr.z),
-                               a3 = unpack_bf16x2(rr.w);
-                  q.x = pack_bf16x2(silu_f(fmaf(a0.x, sc[0], sh[0])), silu_f(fmaf(a0.y, sc[1], sh[1])));
-                  q.y = pack_bf16x2(silu_f(fmaf(a1.x, sc[2], sh[2])), silu_f(fmaf(a1.y, sc[3], sh[3])));
-                  q.z = pack_bf16x2(silu_f(fmaf(a2.x, sc[4], sh[4])), silu_f(fmaf(a2.y, sc[5], sh[5])));
-                  q.w = pack_bf16x2(silu_f(fmaf(a3.x, sc[6], sh[6])), silu_f(fmaf(a3.y, sc[7], sh[7])));
+                if (ok[i]) {
+                  const float2 a0 = unpack_bf16x2(raw[i].x), a1 = unpack_bf16x2(raw[i].y),
+                               a2 = unpack_bf16x2(raw[i].z), a3 = unpack_bf16x2(raw[i].w);
+                  q.x = pack_bf16x2(silu_fast(fmaf(a0.x, sc[0], sh[0])), silu_fast(fmaf(a0.y, sc[1], sh[1])));
+                  q.y = pack_bf16x2(silu_fast(fmaf(a1.x, sc[2], sh[2])), silu_fast(fmaf(a1.y, sc[3], sh[3])));
+                  q.z = pack_bf16x2(silu_fast(fmaf(a2.x, sc[4], sh[4])), silu_fast(fmaf(a2.y, sc[5], sh[5])));
+                  q.w = pack_bf16x2(silu_fast(fmaf(a3.x, sc[6], sh[6])), silu_fast(fmaf(a3.y, sc[7], sh[7])));
                 }
-                *ptr = q;
+                sts128(base + static_cast<uint32_t>(r) * 128u, q);
               }
             }
+            long long f0 = 0;
+            if (p.dbg) f0 = clock64();
             fence_proxy_async_smem();
+            if (p.dbg) x_fence += clock64() - f0;
           }
           __syncwarp();
           if (lane == 0) mbar_arrive_remote_release_cluster(&readyA[sa], 0);
+          if (p.dbg) x_work += clock64() - xq;
           if (++sa == SA) { sa = 0; pa ^= 1u; }
         }
       }
+    }
+    if (p.dbg != nullptr && blockIdx.x == 0 && tx == 0) {
+      p.dbg[14] = x_wait;
+      p.dbg[15] = x_work;
+      p.dbg[12] = x_ld;
+      p.dbg[13] = x_fence;
     }
   }
 
@@ -813,7 +858,7 @@ static int launch_halo(const HaloParams& p, int max_ctas, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(XF ? 320 : 192);
+  cfg.blockDim = dim3(XF ? 480 : 224);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

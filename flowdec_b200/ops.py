@@ -12,8 +12,8 @@ from . import _lib
 # CTA-pair (cta_group::2) convolution tiles; tests flip this to compare both MMA variants
 CTA_PAIRS = True
 # 16x8 "halo" tiles (one A box per k-slice serves all nine taps; needed for fused GroupNorm+SiLU operands).
-# Experimental: measured 5-10 % slower than the per-tap kernel in round 1, so off by default.
-HALO_TILES = False
+# False selects the per-tap kernel (one A box per tap and k-slice).
+HALO_TILES = True
 
 
 def halo_eligible(B, H, W, npad):

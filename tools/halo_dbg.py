@@ -35,3 +35,6 @@ for name, srcs, halo in [("per-tap pair kernel", [(x, 0, C, 9)], False), ("halo 
         line += (f" | block0 MMA thread: total {d[0]} cyc over {d[4]} tiles ({d[0]/max(d[4],1):.0f}/tile; ideal {36*512}), "
                  f"wait tmem-empty {d[1]/d[0]:.1%}, wait A-ready {d[2]/d[0]:.1%}, wait B-full {d[3]/d[0]:.1%}")
     print(line)
+    if halo and d[15]:
+        print(f"      transform warp 7: waits for TMA {d[14]/max(d[4],1):.0f} cyc/tile, transform+publish {d[15]/max(d[4],1):.0f} cyc/tile "
+              f"(of which loads {d[12]/max(d[4],1):.0f}, proxy fence {d[13]/max(d[4],1):.0f})")
