@@ -331,7 +331,7 @@ def main():
             traffic = tj["dram_bytes_per_launch"]
             traffic_note = (f"ncu dram read+write of the dominant launch shape ({tj['launch_shape']}); algorithmic "
                             f"{tj['algorithmic_bytes_per_launch']} B; tensor pipe active {tj['tensor_pipe_active_pct_of_elapsed']} % of elapsed")
-        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
+        roofline = {"bound": "tensor", "kernel": "conv_halo_kernel / conv_igemm_kernel (tcgen05 implicit GEMM, GroupNorm+SiLU operand transform fused)", "achieved": achieved,
                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_note": traffic_note,
                     "peak_source": how, "launches": len(prof), "kernel_ms_per_step": conv_ms,
