@@ -61,6 +61,9 @@ SIGNATURES = {
     "fd_rvq_from_codes": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "fd_dac_conv1d": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "fd_dac_conv_transpose1d": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "fd_dac_conv1d_strided": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "fd_rvq_encode": [_P] * 13 + [_I] * 6 + [_P],
+    "fd_fir_tiles_enable": [_I],
 }
 
 

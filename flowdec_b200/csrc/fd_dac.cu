@@ -23,7 +23,9 @@ __device__ __forceinline__ float snake_f(float x, float a) {
 
 // out[b,co,t] = epi( bias[co] + sum_ci sum_k w[co,ci,k] * act(x[b,ci,t + k*dil - pad]) ) (+ res[b,co,t])
 // act = Snake(alpha[ci]) if alpha != nullptr; epi = tanh if do_tanh.
+// Strided form (encoder down-sampling conv): input index (t*stride + k*dil - pad).
 // block: 256 threads; thread (tx = tid & 15, ty = tid >> 4) owns co = ty*4..+3, t = tx + 16*j (j < 8)
+template <int kCiChunk>
 __global__ void __launch_bounds__(256) dac_conv1d_kernel(const float* __restrict__ x,
                                                          const float* __restrict__ w,
                                                          const float* __restrict__ bias,
@@ -31,9 +33,9 @@ __global__ void __launch_bounds__(256) dac_conv1d_kernel(const float* __restrict
                                                          const float* __restrict__ res,
                                                          float* __restrict__ out, int Cin, int Cout,
                                                          int Tin, int Tout, int K, int dil, int pad,
-                                                         int do_tanh) {
+                                                         int stride, int do_tanh) {
   extern __shared__ float smem[];
-  const int span = kTTile + (K - 1) * dil;           // input samples needed per channel
+  const int span = (kTTile - 1) * stride + (K - 1) * dil + 1;   // input samples needed per channel
   float* sx = smem;                                   // [kCiChunk][span]
   float* sw = smem + kCiChunk * span;                 // [kCiChunk][K][kCoTile]
   const int t0 = blockIdx.x * kTTile, co0 = blockIdx.y * kCoTile, b = blockIdx.z;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(256) dac_conv1d_kernel(const float* __restrict
     __syncthreads();
     for (int i = threadIdx.x; i < kCiChunk * span; i += 256) {
       const int ci = i / span, tt = i - ci * span;
-      const int c = c0 + ci, ti = t0 + tt - pad;
+      const int c = c0 + ci, ti = t0 * stride + tt - pad;
       float v = 0.f;
       if (c < Cin && ti >= 0 && ti < Tin) {
         v = xb[static_cast<size_t>(c) * Tin + ti];
@@ -67,10 +69,10 @@ __global__ void __launch_bounds__(256) dac_conv1d_kernel(const float* __restrict
     for (int ci = 0; ci < kCiChunk; ++ci) {
       for (int k = 0; k < K; ++k) {
         const float4 w4 = *reinterpret_cast<const float4*>(&sw[(ci * K + k) * kCoTile + ty * 4]);
-        const float* xr = sx + ci * span + k * dil + tx;
+        const float* xr = sx + ci * span + k * dil + tx * stride;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xv = xr[16 * j];
+          const float xv = xr[16 * j * stride];
           acc[0][j] = fmaf(w4.x, xv, acc[0][j]);
           acc[1][j] = fmaf(w4.y, xv, acc[1][j]);
           acc[2][j] = fmaf(w4.z, xv, acc[2][j]);
@@ -198,22 +200,177 @@ __global__ void rvq_from_codes_kernel(const long long* __restrict__ codes, const
   }
 }
 
+// ResidualVectorQuantize.forward (eval) — one warp per time column, the running residual and the
+// quantised sum of that column live in shared memory.  Per quantizer i:
+//   e = in_proj_i(res) ; en = e / max(|e|, 1e-12) ; idx = argmax_c -( |en|^2 - 2 en.cn_c + |cn_c|^2 )
+//   (first index wins ties, as torch.max) ; zq_i = out_proj_i(codebook_i[idx]) ; zq += zq_i ; res -= zq_i
+constexpr int kRvqWarps = 4;
+constexpr int kRvqMaxCdim = 16;
+
+__global__ void __launch_bounds__(kRvqWarps * 32) rvq_encode_kernel(
+    const float* __restrict__ z, const float* __restrict__ in_w, const float* __restrict__ in_b,
+    const float* __restrict__ cb, const float* __restrict__ cbn, const float* __restrict__ cb2,
+    const float* __restrict__ out_w, const float* __restrict__ out_b, long long* __restrict__ codes,
+    float* __restrict__ zq, float* __restrict__ latents, float* __restrict__ sqerr, int B, int nq, int T,
+    int D, int cdim, int csize) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * kRvqWarps + warp;           // b * T + t
+  if (col >= B * T) return;
+  const int b = col / T, t = col - b * T;
+  float* res = smem + static_cast<size_t>(warp) * 2 * D;
+  float* acc = res + D;
+  const float* zc = z + static_cast<size_t>(b) * D * T + t;
+  for (int d = lane; d < D; d += 32) {
+    res[d] = zc[static_cast<size_t>(d) * T];
+    acc[d] = 0.f;
+  }
+  __syncwarp();
+  for (int i = 0; i < nq; ++i) {
+    float e[kRvqMaxCdim];
+#pragma unroll
+    for (int j = 0; j < kRvqMaxCdim; ++j) e[j] = 0.f;
+    const float* wi = in_w + static_cast<size_t>(i) * cdim * D;
+    for (int d = lane; d < D; d += 32) {
+      const float r = res[d];
+#pragma unroll
+      for (int j = 0; j < kRvqMaxCdim; ++j)
+        if (j < cdim) e[j] = fmaf(wi[static_cast<size_t>(j) * D + d], r, e[j]);
+    }
+    float n2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRvqMaxCdim; ++j) {
+      if (j < cdim) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e[j] += __shfl_xor_sync(0xffffffffu, e[j], o);
+        e[j] += in_b[i * cdim + j];
+        n2 = fmaf(e[j], e[j], n2);
+        if (lane == j) latents[(static_cast<size_t>(b) * nq * cdim + i * cdim + j) * T + t] = e[j];
+      }
+    }
+    const float inv = 1.f / fmaxf(sqrtf(n2), 1e-12f);
+    float en[kRvqMaxCdim], l2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRvqMaxCdim; ++j) {
+      en[j] = (j < cdim) ? e[j] * inv : 0.f;
+      l2 = fmaf(en[j], en[j], l2);
+    }
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    const float* cni = cbn + static_cast<size_t>(i) * csize * cdim;
+    for (int c = lane; c < csize; c += 32) {
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < kRvqMaxCdim; ++j)
+        if (j < cdim) dot = fmaf(en[j], cni[static_cast<size_t>(c) * cdim + j], dot);
+      const float score = -((l2 - 2.f * dot) + cb2[i * csize + c]);
+      if (score > best) { best = score; bidx = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    const float* ce = cb + (static_cast<size_t>(i) * csize + bidx) * cdim;
+    float q[kRvqMaxCdim], se = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRvqMaxCdim; ++j) {
+      q[j] = (j < cdim) ? ce[j] : 0.f;
+      if (j < cdim) se = fmaf(e[j] - q[j], e[j] - q[j], se);
+    }
+    if (lane == 0) {
+      codes[(static_cast<size_t>(b) * nq + i) * T + t] = bidx;
+      sqerr[(static_cast<size_t>(i) * B + b) * T + t] = se;
+    }
+    const float* wo = out_w + static_cast<size_t>(i) * D * cdim;
+    for (int d = lane; d < D; d += 32) {
+      float v = out_b[static_cast<size_t>(i) * D + d];
+#pragma unroll
+      for (int j = 0; j < kRvqMaxCdim; ++j)
+        if (j < cdim) v = fmaf(wo[static_cast<size_t>(d) * cdim + j], q[j], v);
+      acc[d] += v;
+      res[d] -= v;
+    }
+    __syncwarp();
+  }
+  float* zo = zq + static_cast<size_t>(b) * D * T + t;
+  for (int d = lane; d < D; d += 32) zo[static_cast<size_t>(d) * T] = acc[d];
+}
+
+// commitment / codebook loss of the eval forward: sum_i mean_b mean_{j,t} (z_e - z_q)^2 (one block, fixed order)
+__global__ void __launch_bounds__(256) rvq_loss_kernel(const float* __restrict__ sqerr, float* __restrict__ loss,
+                                                       int n, float scale) {
+  __shared__ double part[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += static_cast<double>(sqerr[i]);
+  part[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = static_cast<float>(part[0] * static_cast<double>(scale));
+}
+
 }  // namespace fd
 
 using namespace fd;
 
+static int launch_dac_conv1d(const float* x, const float* w, const float* bias, const float* snake_alpha,
+                             const float* residual, float* out, int B, int Cin, int Cout, int Tin, int K,
+                             int dilation, int pad, int stride, int do_tanh, cudaStream_t stream,
+                             const char* who) {
+  const int Tout = (Tin + 2 * pad - dilation * (K - 1) - 1) / stride + 1;
+  FD_REQUIRE(Tin + 2 * pad - dilation * (K - 1) >= 1 && K >= 1 && K <= 16 && stride >= 1 && stride <= 16,
+             "%s: bad geometry (Tin=%d, K=%d, stride=%d)", who, Tin, K, stride);
+  const int span = (kTTile - 1) * stride + (K - 1) * dilation + 1;
+  const int ci = stride == 1 ? kCiChunk : 4;         // strided spans are long: stage fewer channels per step
+  const size_t smem = (static_cast<size_t>(ci) * span + ci * K * kCoTile) * sizeof(float);
+  FD_REQUIRE(smem <= 48 * 1024, "%s: K*dilation / stride too large for the staging buffer", who);
+  dim3 grid((Tout + kTTile - 1) / kTTile, (Cout + kCoTile - 1) / kCoTile, B);
+  if (stride == 1)
+    dac_conv1d_kernel<kCiChunk><<<grid, 256, smem, stream>>>(x, w, bias, snake_alpha, residual, out, Cin, Cout,
+                                                             Tin, Tout, K, dilation, pad, 1, do_tanh);
+  else
+    dac_conv1d_kernel<4><<<grid, 256, smem, stream>>>(x, w, bias, snake_alpha, residual, out, Cin, Cout, Tin,
+                                                      Tout, K, dilation, pad, stride, do_tanh);
+  return check_launch(who);
+}
+
 extern "C" int fd_dac_conv1d(const float* x, const float* w, const float* bias, const float* snake_alpha,
                              const float* residual, float* out, int B, int Cin, int Cout, int Tin, int K,
                              int dilation, int pad, int do_tanh, cudaStream_t stream) {
-  const int Tout = Tin + 2 * pad - dilation * (K - 1);
-  FD_REQUIRE(Tout > 0 && K >= 1 && K <= 16, "fd_dac_conv1d: bad geometry (Tout=%d, K=%d)", Tout, K);
-  const int span = kTTile + (K - 1) * dilation;
-  const size_t smem = (static_cast<size_t>(kCiChunk) * span + kCiChunk * K * kCoTile) * sizeof(float);
-  FD_REQUIRE(smem <= 48 * 1024, "fd_dac_conv1d: K*dilation too large for the staging buffer");
-  dim3 grid((Tout + kTTile - 1) / kTTile, (Cout + kCoTile - 1) / kCoTile, B);
-  dac_conv1d_kernel<<<grid, 256, smem, stream>>>(x, w, bias, snake_alpha, residual, out, Cin, Cout, Tin,
-                                                 Tout, K, dilation, pad, do_tanh);
-  return check_launch("fd_dac_conv1d");
+  return launch_dac_conv1d(x, w, bias, snake_alpha, residual, out, B, Cin, Cout, Tin, K, dilation, pad, 1,
+                           do_tanh, stream, "fd_dac_conv1d");
+}
+
+extern "C" int fd_dac_conv1d_strided(const float* x, const float* w, const float* bias,
+                                     const float* snake_alpha, float* out, int B, int Cin, int Cout, int Tin,
+                                     int K, int stride, int pad, cudaStream_t stream) {
+  return launch_dac_conv1d(x, w, bias, snake_alpha, nullptr, out, B, Cin, Cout, Tin, K, 1, pad, stride, 0,
+                           stream, "fd_dac_conv1d_strided");
+}
+
+extern "C" int fd_rvq_encode(const float* z, const float* in_proj_w, const float* in_proj_b,
+                             const float* codebooks, const float* codebooks_l2n, const float* codebooks_l2n_sq,
+                             const float* out_proj_w, const float* out_proj_b, long long* codes, float* zq,
+                             float* latents, float* loss, float* sqerr_ws, int B, int nq, int T, int D,
+                             int codebook_dim, int codebook_size, cudaStream_t stream) {
+  FD_REQUIRE(codebook_dim >= 1 && codebook_dim <= kRvqMaxCdim, "fd_rvq_encode: codebook_dim %d > %d",
+             codebook_dim, kRvqMaxCdim);
+  FD_REQUIRE(B >= 1 && nq >= 1 && T >= 1 && codebook_size >= 1, "fd_rvq_encode: empty problem");
+  const size_t smem = static_cast<size_t>(kRvqWarps) * 2 * D * sizeof(float);
+  FD_REQUIRE(smem <= 48 * 1024, "fd_rvq_encode: latent dim %d too large for the column buffers", D);
+  const int cols = B * T;
+  rvq_encode_kernel<<<(cols + kRvqWarps - 1) / kRvqWarps, kRvqWarps * 32, smem, stream>>>(
+      z, in_proj_w, in_proj_b, codebooks, codebooks_l2n, codebooks_l2n_sq, out_proj_w, out_proj_b, codes, zq,
+      latents, sqerr_ws, B, nq, T, D, codebook_dim, codebook_size);
+  int rc = check_launch("fd_rvq_encode");
+  if (rc != 0 || loss == nullptr) return rc;
+  rvq_loss_kernel<<<1, 256, 0, stream>>>(sqerr_ws, loss, nq * B * T,
+                                         1.f / (static_cast<float>(codebook_dim) * T * B));
+  return check_launch("fd_rvq_encode(loss)");
 }
 
 extern "C" int fd_dac_conv_transpose1d(const float* x, const float* w, const float* bias,

@@ -706,6 +706,15 @@ static inline int grid_for(size_t total, int block) {
 }  // namespace fd
 
 using namespace fd;
+
+namespace fd {   // fd_fir_tiles.cu
+bool fir_tiles_eligible(int C1, int C2, int H, int W, int mode);
+int fir_tiles_launch(const void* src1, int C1, const void* src2, int C2, const float* scale_shift, void* out,
+                     void* out_raw, int B, int H, int W, int mode, cudaStream_t stream);
+int fir_tiles_set(int on);
+}  // namespace fd
+
+extern "C" int fd_fir_tiles_enable(int on) { return fir_tiles_set(on); }
 typedef __nv_bfloat16 bf16;
 
 extern "C" int fd_chan_stats(const void* x, int B, int HW, int C, float* partial, int S,
@@ -742,6 +751,8 @@ extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, in
   FD_REQUIRE(out != nullptr || out_raw != nullptr, "fd_gn_act_resample: no output");
   FD_REQUIRE(out == nullptr || scale_shift != nullptr, "fd_gn_act_resample: activated output needs scale_shift");
   FD_REQUIRE(mode != 0 || out != nullptr, "fd_gn_act_resample: mode 0 without activation is a copy");
+  if (out != nullptr && out_raw != nullptr && fir_tiles_eligible(C1, C2, H, W, mode))
+    return fir_tiles_launch(src1, C1, src2, C2, scale_shift, out, out_raw, B, H, W, mode, stream);
   const int oct = (C1 + C2) / 8;
   const int slices = (C1 + C2) / 4;   // FIR variants: 4 channels per thread
   const int UW = mode == 1 ? W / 4 : W;

@@ -1,19 +1,20 @@
-"""Upstream NDAC (DAC) decode path on B200.
+"""Upstream NDAC (DAC) codec on B200 (SURVEY.md §8 a11 decode, §8f-1 encode).
 
 API mirror of the part of descript-audio-codec 1.0.0 the reference's demo uses
 (/root/reference/demo.ipynb:56,101-105):
 
     dac_model = DAC.load(".../weights.pth"); dac_model.to("cuda"); dac_model.eval()
+    x = dac_model.preprocess(signal.audio_data, signal.sample_rate)
+    z, codes, latents, _, _ = dac_model.encode(x, n_quantizers=nq)
     zq, _, _ = dac_model.quantizer.from_codes(codes)
     xhat_ndac = dac_model.decode(zq)
 
 `weights.pth` is audiotools' `{"state_dict": ..., "metadata": {"kwargs": {...}}}`; every
 hyper-parameter (decoder_dim, decoder_rates, n_codebooks, codebook_size, codebook_dim,
 latent_dim / encoder_dim + encoder_rates, sample_rate) comes from that metadata.  Weight-norm
-(`weight_g`, `weight_v`) is folded once at load.  The encoder (`preprocess`/`encode`) is the next
-row to build and raises NotImplementedError.
+(`weight_g`, `weight_v`) is folded and the codebooks are L2-normalised once at load.
 
-All arithmetic of from_codes/decode runs in csrc/fd_dac.cu; there is no fallback.
+All arithmetic of encode / from_codes / decode runs in csrc/fd_dac.cu; there is no fallback.
 """
 import math
 
@@ -48,9 +49,34 @@ class _Quantizer:
         _lib.check(rc, "fd_rvq_from_codes")
         return z, None, codes
 
+    def __call__(self, z, n_quantizers=None):
+        """ResidualVectorQuantize.forward, eval mode (dac/nn/quantize.py): z [B, D, T] ->
+        (z_q [B,D,T], codes int64 [B,n_q,T], latents [B,n_q*cdim,T], commitment_loss, codebook_loss)"""
+        o = self._o
+        o._require_cuda()
+        if o.in_proj_w is None:
+            raise RuntimeError("this checkpoint has no quantizer in_proj weights (decode-only state_dict)")
+        z = z.to(o.device, torch.float32).contiguous()
+        B, D, T = z.shape
+        if D != o.latent_dim:
+            raise ValueError(f"latent has {D} channels, model expects {o.latent_dim}")
+        nq = o.n_codebooks if n_quantizers is None else max(1, min(int(n_quantizers), o.n_codebooks))
+        codes = torch.empty(B, nq, T, device=o.device, dtype=torch.int64)
+        zq = torch.empty_like(z)
+        latents = torch.empty(B, nq * o.codebook_dim, T, device=o.device, dtype=torch.float32)
+        loss = torch.empty(1, device=o.device, dtype=torch.float32)
+        ws = torch.empty(nq * B * T, device=o.device, dtype=torch.float32)
+        rc = _lib.lib().fd_rvq_encode(_lib.ptr(z), _lib.ptr(o.in_proj_w), _lib.ptr(o.in_proj_b),
+                                      _lib.ptr(o.codebooks), _lib.ptr(o.codebooks_l2n), _lib.ptr(o.codebooks_l2n_sq),
+                                      _lib.ptr(o.out_proj_w), _lib.ptr(o.out_proj_b), _lib.ptr(codes), _lib.ptr(zq),
+                                      _lib.ptr(latents), _lib.ptr(loss), _lib.ptr(ws), B, nq, T, D, o.codebook_dim,
+                                      o.codebook_size, _lib.stream_ptr())
+        _lib.check(rc, "fd_rvq_encode")
+        return zq, codes, latents, loss[0], loss[0].clone()
+
 
 class DAC(nn.Module):
-    """decode half of dac.DAC (dac/model/dac.py) running on hand-written CUDA kernels"""
+    """dac.DAC (dac/model/dac.py) inference — preprocess / encode / quantizer / decode — on hand-written CUDA kernels"""
 
     def __init__(self, state_dict, decoder_dim=1536, decoder_rates=(8, 8, 4, 2), n_codebooks=9,
                  codebook_size=1024, codebook_dim=8, latent_dim=None, encoder_dim=64,
@@ -60,7 +86,8 @@ class DAC(nn.Module):
         self.n_codebooks, self.codebook_size, self.codebook_dim = int(n_codebooks), int(codebook_size), int(codebook_dim)
         self.latent_dim = int(latent_dim) if latent_dim is not None else int(encoder_dim * 2 ** len(encoder_rates))
         self.sample_rate = int(sample_rate)
-        self.hop_length = int(np.prod(self.decoder_rates))
+        self.encoder_dim, self.encoder_rates = int(encoder_dim), [int(r) for r in encoder_rates]
+        self.hop_length = int(np.prod(self.encoder_rates))
         sd = state_dict
         # --- RVQ tables
         self.register_buffer("codebooks", torch.stack(
@@ -69,6 +96,17 @@ class DAC(nn.Module):
             [_fold_weight_norm(sd, f"quantizer.quantizers.{i}.out_proj").squeeze(-1) for i in range(self.n_codebooks)]).contiguous())
         self.register_buffer("out_proj_b", torch.stack(
             [sd[f"quantizer.quantizers.{i}.out_proj.bias"].float() for i in range(self.n_codebooks)]).contiguous())
+        has_in = "quantizer.quantizers.0.in_proj.weight_v" in sd
+        self.register_buffer("in_proj_w", torch.stack(
+            [_fold_weight_norm(sd, f"quantizer.quantizers.{i}.in_proj").squeeze(-1) for i in range(self.n_codebooks)]
+        ).contiguous() if has_in else None)
+        self.register_buffer("in_proj_b", torch.stack(
+            [sd[f"quantizer.quantizers.{i}.in_proj.bias"].float() for i in range(self.n_codebooks)]
+        ).contiguous() if has_in else None)
+        # VectorQuantize.decode_latents compares L2-normalised rows: normalise the tables once (F.normalize, eps 1e-12)
+        cbn = self.codebooks / self.codebooks.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        self.register_buffer("codebooks_l2n", cbn.contiguous())
+        self.register_buffer("codebooks_l2n_sq", cbn.pow(2).sum(-1).contiguous())
         # --- decoder layers as a flat op list
         self._ops = []
         m = "decoder.model."
@@ -98,6 +136,29 @@ class DAC(nn.Module):
         a = reg(f"{m}{n + 1}.alpha", sd[f"{m}{n + 1}.alpha"].reshape(-1))
         w, b = conv(f"{m}{n + 2}")
         self._ops.append(("conv", w, b, a, 1, 3, False, True))
+        # --- encoder layers (dac/model/dac.py Encoder / EncoderBlock), present in full checkpoints
+        self._enc_ops = None
+        e = "encoder.block."
+        if e + "0.weight_v" in sd:
+            self._enc_ops = []
+            w, b = conv(e + "0")
+            self._enc_ops.append(("conv", w, b, None, 1, 3, False, False))
+            for i, s in enumerate(self.encoder_rates):
+                blk = f"{e}{i + 1}.block."
+                for j, d in enumerate((1, 3, 9)):
+                    r = f"{blk}{j}.block."
+                    a1 = reg(r + "0.alpha", sd[r + "0.alpha"].reshape(-1))
+                    w1, b1 = conv(r + "1")
+                    a2 = reg(r + "2.alpha", sd[r + "2.alpha"].reshape(-1))
+                    w2, b2 = conv(r + "3")
+                    self._enc_ops.append(("res", (w1, b1, a1, d), (w2, b2, a2)))
+                a = reg(blk + "3.alpha", sd[blk + "3.alpha"].reshape(-1))
+                w, b = conv(blk + "4")
+                self._enc_ops.append(("down", w, b, a, s, math.ceil(s / 2)))
+            n = len(self.encoder_rates)
+            a = reg(f"{e}{n + 1}.alpha", sd[f"{e}{n + 1}.alpha"].reshape(-1))
+            w, b = conv(f"{e}{n + 2}")
+            self._enc_ops.append(("conv", w, b, a, 1, 1, False, False))
         self.quantizer = _Quantizer(self)
 
     @property
@@ -127,12 +188,8 @@ class DAC(nn.Module):
         _lib.check(rc, "fd_dac_conv1d")
         return out
 
-    @torch.no_grad()
-    def decode(self, z):
-        """z [B, latent_dim, T] -> waveform [B, 1, ~T*hop] (dac.DAC.decode, demo.ipynb:105)"""
-        self._require_cuda()
-        x = z.to(self.device, torch.float32).contiguous()
-        for op in self._ops:
+    def _run(self, ops_list, x):
+        for op in ops_list:
             if op[0] == "conv":
                 _, w, b, a, dil, pad, _, tanh = op
                 x = self._conv(x, w, b, a, dil, pad, tanh=tanh)
@@ -146,13 +203,58 @@ class DAC(nn.Module):
                                                         _lib.ptr(out), B, Cin, Cout, Tin, s, pad, _lib.stream_ptr())
                 _lib.check(rc, "fd_dac_conv_transpose1d")
                 x = out
+            elif op[0] == "down":
+                _, w, b, a, s, pad = op
+                B, Cin, Tin = x.shape
+                Cout, _, K = w.shape
+                Tout = (Tin + 2 * pad - K) // s + 1
+                out = torch.empty(B, Cout, Tout, device=x.device, dtype=torch.float32)
+                rc = _lib.lib().fd_dac_conv1d_strided(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(a),
+                                                      _lib.ptr(out), B, Cin, Cout, Tin, K, s, pad, _lib.stream_ptr())
+                _lib.check(rc, "fd_dac_conv1d_strided")
+                x = out
             else:
                 _, (w1, b1, a1, d), (w2, b2, a2) = op
                 y = self._conv(x, w1, b1, a1, d, 3 * d)
                 x = self._conv(y, w2, b2, a2, 1, 0, res=x)
         return x
 
-    def preprocess(self, *a, **k):
-        raise NotImplementedError("NDAC encoder side (preprocess/encode) is the next row to build (SURVEY.md §8f-1)")
+    @torch.no_grad()
+    def decode(self, z):
+        """z [B, latent_dim, T] -> waveform [B, 1, ~T*hop] (dac.DAC.decode, demo.ipynb:105)"""
+        self._require_cuda()
+        return self._run(self._ops, z.to(self.device, torch.float32).contiguous())
 
-    encode = preprocess
+    def preprocess(self, audio_data, sample_rate=None):
+        """dac.DAC.preprocess (demo.ipynb:101): zero-pad on the right to a multiple of hop_length.
+        Pure data movement (no arithmetic)."""
+        if sample_rate is None:
+            sample_rate = self.sample_rate
+        assert sample_rate == self.sample_rate, f"expected {self.sample_rate} Hz audio, got {sample_rate}"
+        L = audio_data.shape[-1]
+        right = math.ceil(L / self.hop_length) * self.hop_length - L
+        if right == 0:
+            return audio_data
+        out = audio_data.new_zeros(*audio_data.shape[:-1], L + right)
+        out[..., :L].copy_(audio_data)
+        return out
+
+    @torch.no_grad()
+    def encode(self, audio_data, n_quantizers=None):
+        """dac.DAC.encode (demo.ipynb:102): audio [B, 1, L] (L a multiple of hop_length) ->
+        (z_q [B,D,T], codes [B,n_q,T], latents [B,n_q*cdim,T], commitment_loss, codebook_loss)"""
+        self._require_cuda()
+        if self._enc_ops is None:
+            raise RuntimeError("this checkpoint has no encoder weights (decode-only state_dict)")
+        x = audio_data.to(self.device, torch.float32).contiguous()
+        if x.ndim != 3 or x.shape[1] != 1:
+            raise ValueError(f"audio_data must be [B, 1, L], got {tuple(x.shape)}")
+        return self.quantizer(self._run(self._enc_ops, x), n_quantizers)
+
+    @torch.no_grad()
+    def forward(self, audio_data, sample_rate=None, n_quantizers=None):
+        """dac.DAC.forward: preprocess -> encode -> decode, audio cropped back to the input length"""
+        L = audio_data.shape[-1]
+        z, codes, latents, commit, cbl = self.encode(self.preprocess(audio_data, sample_rate), n_quantizers)
+        return {"audio": self.decode(z)[..., :L], "z": z, "codes": codes, "latents": latents,
+                "vq/commitment_loss": commit, "vq/codebook_loss": cbl}

@@ -142,6 +142,11 @@ def gn_act_resample(srcs, scale_shift, out, mode, out_raw=None):
     return out
 
 
+def fir_tiles_enable(on):
+    """TMA-tiled up / down kernels (fd_fir_tiles.cu) on/off; returns the previous setting"""
+    return bool(_lib.lib().fd_fir_tiles_enable(int(bool(on))))
+
+
 def pack4(x, y, out):
     n = x.numel() // 2
     _lib.check(_lib.lib().fd_pack4(_lib.ptr(x), _lib.ptr(y), _lib.ptr(out), ctypes.c_size_t(n),

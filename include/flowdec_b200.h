@@ -81,6 +81,9 @@ int fd_gn_finalize(const float* part1, int C1, int S1, const float* part2, int C
  * 2 up x2 ([1,3,3,1]/4, pad (2,1)); outputs bf16 NHWC [B,H',W',C1+C2] */
 int fd_gn_act_resample(const void* src1, int C1, const void* src2, int C2, const float* scale_shift,
                        void* out, void* out_raw, int B, int H, int W, int mode, fd_stream_t stream);
+/* the up / down variants with both outputs run as TMA-tiled kernels (fd_fir_tiles.cu) when C1, C2 % 64 == 0,
+ * H % 8 == 0, W % 16 == 0; fd_fir_tiles_enable(0) forces the register kernels (returns the previous setting) */
+int fd_fir_tiles_enable(int on);
 
 /* ---- 4-channel paths of NCSN++ ---------------------------------------------------------------*/
 /* ncsnpp.py:261,401-404: (re x, im x, re y, im y) -> fp32 [npix,4] */
@@ -142,6 +145,23 @@ int fd_rvq_from_codes(const long long* codes, const float* codebooks, const floa
 int fd_dac_conv1d(const float* x, const float* w, const float* bias, const float* snake_alpha,
                   const float* residual, float* out, int B, int Cin, int Cout, int Tin, int K, int dilation,
                   int pad, int do_tanh, fd_stream_t stream);
+/* encoder down-sampling conv (dac/model/dac.py EncoderBlock: Snake1d -> WNConv1d(k = 2*stride, stride,
+ * padding ceil(stride/2))): out[b,co,t] = bias[co] + sum w[co,ci,k] * snake(x[b,ci,t*stride + k - pad]) */
+int fd_dac_conv1d_strided(const float* x, const float* w, const float* bias, const float* snake_alpha,
+                          float* out, int B, int Cin, int Cout, int Tin, int K, int stride, int pad,
+                          fd_stream_t stream);
+/* dac.nn.quantize.ResidualVectorQuantize.forward in eval mode with n_quantizers = nq (demo.ipynb:102 via
+ * DAC.encode): per quantizer z_e = in_proj_i(residual); nearest code between the L2-normalised z_e and the
+ * L2-normalised codebook (VectorQuantize.decode_latents; first index wins ties); z_q_i = out_proj_i(code).
+ * z, zq [B,D,T]; in_proj_w [nq_total,cdim,D]; in_proj_b [nq_total,cdim]; codebooks / codebooks_l2n
+ * [nq_total,csize,cdim] (raw / row-normalised); codebooks_l2n_sq [nq_total,csize] = |row|^2 of the normalised
+ * table; out_proj_w [nq_total,D,cdim]; out_proj_b [nq_total,D]; codes int64 [B,nq,T]; latents [B,nq*cdim,T];
+ * loss [1] or NULL = commitment (= codebook) loss; sqerr_ws workspace [nq*B*T] floats */
+int fd_rvq_encode(const float* z, const float* in_proj_w, const float* in_proj_b, const float* codebooks,
+                  const float* codebooks_l2n, const float* codebooks_l2n_sq, const float* out_proj_w,
+                  const float* out_proj_b, long long* codes, float* zq, float* latents, float* loss,
+                  float* sqerr_ws, int B, int nq, int T, int D, int codebook_dim, int codebook_size,
+                  fd_stream_t stream);
 /* Snake1d -> WNConvTranspose1d(kernel 2*stride, stride, padding pad); w [Cin,Cout,2*stride] */
 int fd_dac_conv_transpose1d(const float* x, const float* w, const float* bias, const float* snake_alpha,
                             float* out, int B, int Cin, int Cout, int Tin, int stride, int pad,

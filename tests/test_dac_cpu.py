@@ -53,3 +53,57 @@ def test_dac_oracle_vs_transformers_port():
         x = D.decode(sd, z, rates)
     assert x.shape == x_ref.shape
     assert torch.allclose(x, x_ref, rtol=1e-4, atol=1e-5), (x - x_ref).abs().max()
+
+
+def _hf_encoder(sd, latent, edim, erates, nq):
+    from transformers.models.dac.configuration_dac import DacConfig
+    cfg = DacConfig(encoder_hidden_size=edim, downsampling_ratios=list(erates), hidden_size=latent, n_codebooks=nq,
+                    codebook_size=1024, codebook_dim=8)
+    enc = tdac.DacEncoder(cfg).eval()
+    rvq = tdac.DacResidualVectorQuantizer(cfg).eval()
+
+    def cp(mod, p):
+        mod.weight.copy_(D.wn(sd, p)); mod.bias.copy_(sd[p + ".bias"])
+
+    with torch.no_grad():
+        e = "encoder.block."
+        cp(enc.conv1, e + "0")
+        for i in range(len(erates)):
+            b = f"{e}{i + 1}.block."
+            blk = enc.block[i]
+            for j, ru in enumerate((blk.res_unit1, blk.res_unit2, blk.res_unit3)):
+                r = f"{b}{j}.block."
+                ru.snake1.alpha.copy_(sd[r + "0.alpha"]); cp(ru.conv1, r + "1")
+                ru.snake2.alpha.copy_(sd[r + "2.alpha"]); cp(ru.conv2, r + "3")
+            blk.snake1.alpha.copy_(sd[b + "3.alpha"]); cp(blk.conv1, b + "4")
+        n = len(erates)
+        enc.snake1.alpha.copy_(sd[f"{e}{n + 1}.alpha"]); cp(enc.conv2, f"{e}{n + 2}")
+        for i in range(nq):
+            q = f"quantizer.quantizers.{i}."
+            rvq.quantizers[i].codebook.weight.copy_(sd[q + "codebook.weight"])
+            cp(rvq.quantizers[i].in_proj, q + "in_proj")
+            cp(rvq.quantizers[i].out_proj, q + "out_proj")
+    return enc, rvq
+
+
+def test_dac_encode_oracle_vs_transformers_port():
+    """§8f-1: Encoder + ResidualVectorQuantize.forward (eval) restatement vs the transformers port"""
+    latent, dim, rates, nq, edim, erates = 64, 96, (4, 3, 2), 5, 8, (2, 3, 4)
+    sd = D.synth_dac_state_dict(latent, dim, rates, nq, seed=1, encoder_dim=edim, encoder_rates=erates)
+    enc, rvq = _hf_encoder(sd, latent, edim, erates, nq)
+    g = torch.Generator().manual_seed(3)
+    x = D.preprocess(0.3 * torch.randn(2, 1, 1000, generator=g), 24)
+    assert x.shape[-1] == 1008
+    with torch.no_grad():
+        z_ref = enc(x)
+        z = D.encode(sd, x, erates)
+        assert z.shape == z_ref.shape == (2, latent, 42)
+        assert torch.allclose(z, z_ref, rtol=1e-4, atol=1e-5), (z - z_ref).abs().max()
+        for n_q in (None, 3):
+            zq_ref, codes_ref, lat_ref, commit_ref, cb_ref = rvq(z_ref, n_q)
+            zq, codes, lat, commit, cbl, margin = D.rvq_encode(sd, z_ref, n_q)
+            assert codes.shape == codes_ref.shape and torch.equal(codes, codes_ref)
+            assert torch.allclose(zq, zq_ref, rtol=1e-4, atol=1e-5)
+            assert torch.allclose(lat, lat_ref, rtol=1e-4, atol=1e-5)
+            assert torch.allclose(commit, commit_ref.mean(), rtol=1e-4) and torch.allclose(cbl, cb_ref.mean(), rtol=1e-4)
+            assert (margin >= 0).all()

@@ -92,3 +92,96 @@ def test_from_codes_and_decode(latent, dim, rates, nq, T):
     # fewer codebooks than the model has (bitrate scalability, demo.ipynb:85-88)
     zq2, _, _ = model.quantizer.from_codes(codes[:, :3])
     assert rel(zq2.cpu(), D.from_codes(sd, codes[:, :3])) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# encode half: strided conv, RVQ encode, DAC.preprocess / encode / forward
+@pytest.mark.parametrize("Cin,Cout,s,T", [(8, 16, 2, 1000), (64, 128, 4, 517), (96, 192, 8, 2048), (32, 64, 3, 301),
+                                          (128, 256, 8, 130)])
+def test_conv1d_strided_snake(Cin, Cout, s, T):
+    torch.manual_seed(3)
+    B, K, pad = 2, 2 * s, math.ceil(s / 2)
+    x = torch.randn(B, Cin, T)
+    w = torch.randn(Cout, Cin, K) / math.sqrt(Cin * K)
+    b = torch.randn(Cout) * 0.1
+    alpha = torch.rand(Cin) + 0.5
+    ref = F.conv1d(D.snake(x, alpha.reshape(1, -1, 1)), w, b, stride=s, padding=pad)
+    out = torch.empty(B, Cout, ref.shape[-1], device="cuda")
+    c = lambda t: t.cuda().contiguous()
+    xd, wd, bd, ad = c(x), c(w), c(b), c(alpha)
+    rc = _lib.lib().fd_dac_conv1d_strided(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(ad), _lib.ptr(out),
+                                          B, Cin, Cout, T, K, s, pad, _lib.stream_ptr())
+    _lib.check(rc, "fd_dac_conv1d_strided")
+    assert rel(out.cpu(), ref) < 1e-5
+
+
+def _check_codes(codes_gpu, z_in, sd, n_q):
+    """index parity with the oracle on the SAME latent; a differing index is only accepted where the oracle's
+    own best/second-best margin is below fp32 resolution of the distance (and then later stages of that
+    column legitimately diverge, so the comparison stops at the first such quantizer)."""
+    zq_o, codes_o, lat_o, commit_o, _, margin = D.rvq_encode(sd, z_in, n_q)
+    cg = codes_gpu.cpu()
+    assert cg.shape == codes_o.shape and cg.dtype == torch.int64
+    B, nq, T = cg.shape
+    diverged = torch.zeros(B, T, dtype=torch.bool)
+    n_bad = 0
+    for i in range(nq):
+        diff = (cg[:, i] != codes_o[:, i]) & ~diverged
+        assert (margin[:, i][diff] < 2e-6).all(), f"quantizer {i}: index differs with margin {margin[:, i][diff].max()}"
+        n_bad += int(diff.sum())
+        diverged |= diff
+    return zq_o, codes_o, lat_o, commit_o, diverged, n_bad
+
+
+@pytest.mark.parametrize("B,D_,T,nq_total,n_q", [(2, 64, 42, 5, None), (3, 1024, 173, 9, 9), (1, 128, 1, 4, 2),
+                                                  (2, 256, 90, 16, 16)])
+def test_rvq_encode(B, D_, T, nq_total, n_q):
+    sd = D.synth_dac_state_dict(D_, 32, (2,), nq_total, seed=4)
+    model = DAC(sd, decoder_dim=32, decoder_rates=(2,), n_codebooks=nq_total, latent_dim=D_).to("cuda").eval()
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(B, D_, T, generator=g)
+    zq, codes, latents, commit, cbl = model.quantizer(z.cuda(), n_q)
+    zq_o, codes_o, lat_o, commit_o, diverged, n_bad = _check_codes(codes, z, sd, n_q)
+    ok = ~diverged
+    print(f"\nRVQ encode: {int(ok.sum())}/{ok.numel()} columns index-identical through all quantizers "
+          f"({n_bad} near-tie flips)")
+    assert ok.float().mean() > 0.98
+    assert rel(zq.cpu().transpose(1, 2)[ok], zq_o.transpose(1, 2)[ok]) < 1e-5
+    assert rel(latents.cpu().transpose(1, 2)[ok], lat_o.transpose(1, 2)[ok]) < 1e-4
+    if ok.all():
+        assert abs(commit.item() - commit_o.item()) <= 1e-4 * abs(commit_o.item())
+        assert cbl.item() == commit.item()
+        # from_codes(encode(z).codes) reproduces z_q: the decode-side entry point and the encoder agree
+        assert rel(model.quantizer.from_codes(codes)[0], zq) < 1e-6
+
+
+def test_dac_preprocess_encode_decode():
+    latent, dim, rates, nq, edim, erates = 64, 96, (4, 3, 2), 6, 8, (2, 3, 4)
+    sd = D.synth_dac_state_dict(latent, dim, rates, nq, seed=1, encoder_dim=edim, encoder_rates=erates)
+    model = DAC(sd, decoder_dim=dim, decoder_rates=rates, n_codebooks=nq, latent_dim=latent, encoder_dim=edim,
+                encoder_rates=erates, sample_rate=48000).to("cuda").eval()
+    assert model.hop_length == 24
+    g = torch.Generator().manual_seed(6)
+    audio = 0.3 * torch.randn(3, 1, 4001, generator=g)
+    x = model.preprocess(audio.cuda(), 48000)
+    assert x.shape[-1] == 4008 and torch.equal(x[..., :4001].cpu(), audio) and (x[..., 4001:] == 0).all()
+    with pytest.raises(AssertionError):
+        model.preprocess(audio, 44100)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    with torch.no_grad():
+        z32 = D.encode(sd, x.cpu(), erates)
+        z64 = D.encode(sd64, x.cpu().double(), erates)
+    z_gpu = model._run(model._enc_ops, x)
+    r, r32 = rel(z_gpu.cpu(), z64), rel(z32, z64)
+    print(f"\nNDAC encoder rel-L2 vs fp64 oracle: gpu {r:.3e}, cpu fp32 {r32:.3e}")
+    assert z_gpu.shape == z64.shape and r <= 3 * r32 + 1e-5
+    # encode(): codes are checked against the oracle quantizer run on the GPU's own encoder output
+    zq, codes, latents, commit, _ = model.encode(x, n_quantizers=4)
+    assert codes.shape == (3, 4, 167) and latents.shape == (3, 32, 167)
+    zq_o, codes_o, _, _, diverged, _ = _check_codes(codes, z_gpu.cpu(), sd, 4)
+    assert (~diverged).float().mean() > 0.98
+    ok = ~diverged
+    assert rel(zq.cpu().transpose(1, 2)[ok], zq_o.transpose(1, 2)[ok]) < 1e-5
+    out = model(audio.cuda(), 48000, n_quantizers=4)
+    assert out["audio"].shape == audio.shape and torch.equal(out["codes"], codes)
+    assert rel(out["audio"], model.decode(zq)[..., :4001]) == 0.0

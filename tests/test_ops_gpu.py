@@ -73,6 +73,48 @@ def test_groupnorm_silu_resample(C1, C2, mode):
         assert e2 <= 2 ** -8 * r.abs().max().item() + 1e-3, e2
 
 
+@pytest.mark.parametrize("B,H,W,C1,C2,mode", [(2, 16, 32, 64, 0, 2), (2, 16, 32, 64, 0, 1), (1, 24, 48, 128, 64, 2),
+                                              (1, 24, 48, 128, 64, 1), (4, 128, 64, 256, 0, 1), (2, 64, 64, 256, 0, 2),
+                                              (1, 8, 16, 64, 64, 2), (1, 8, 16, 64, 64, 1)])
+def test_fir_tile_kernels(B, H, W, C1, C2, mode):
+    """TMA-tiled GroupNorm+SiLU+FIR kernels (fd_fir_tiles.cu) vs the oracle and vs the register kernels;
+    the largest cases give every persistent block several tiles (both ring stages wrap)."""
+    torch.manual_seed(2)
+    C = C1 + C2
+    x1 = torch.randn(B, C1, H, W) * 1.5 + 0.3
+    x2 = torch.randn(B, C2, H, W) * 0.7 if C2 else None
+    gamma, beta = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    srcs = [nhwc_bf16(x1).to(DEV)] + ([nhwc_bf16(x2).to(DEV)] if C2 else [])
+    parts = [ops.chan_stats(s, 8) for s in srcs]
+    ss = torch.empty(B, C, 2, device=DEV)
+    ops.gn_finalize(parts, [s.shape[3] for s in srcs], H * W, gamma.to(DEV), beta.to(DEV), min(C // 4, 32), 1e-6, ss)
+    Ho, Wo = (H // 2, W // 2) if mode == 1 else (2 * H, 2 * W)
+    out = torch.full((B, Ho, Wo, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    raw = torch.full_like(out, float("nan"))
+    assert ops.fir_tiles_enable(True) in (True, False)
+    ops.gn_act_resample(srcs, ss, out, mode, out_raw=raw)
+    prev = ops.fir_tiles_enable(False)
+    assert prev is True
+    try:
+        out_r, raw_r = torch.empty_like(out), torch.empty_like(raw)
+        ops.gn_act_resample(srcs, ss, out_r, mode, out_raw=raw_r)
+    finally:
+        ops.fir_tiles_enable(True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(raw.float()).all()
+    xc = torch.cat([nchw_f32(s.cpu()) for s in srcs], 1)
+    h = F.silu(F.group_norm(xc, min(C // 4, 32), gamma, beta, eps=1e-6))
+    h, r = (O.fir_down2(h), O.fir_down2(xc)) if mode == 1 else (O.fir_up2(h), O.fir_up2(xc))
+    e1 = (nchw_f32(out.cpu()) - h).abs().max().item()
+    e2 = (nchw_f32(raw.cpu()) - r).abs().max().item()
+    assert e1 <= 2 ** -8 * h.abs().max().item() + 1e-3, e1
+    assert e2 <= 2 ** -8 * r.abs().max().item() + 1e-3, e2
+    # same fp32 arithmetic up to summation order: at most one bf16 ulp apart from the register kernels
+    assert (out.float() - out_r.float()).abs().max().item() <= 2 ** -7 * h.abs().max().item()
+    assert (raw.float() - raw_r.float()).abs().max().item() <= 2 ** -7 * r.abs().max().item()
+    assert (out != out_r).float().mean().item() < 0.05
+
+
 def test_conv_in_combine_pyramid_output():
     torch.manual_seed(1)
     B, H, W = 2, 32, 16
