@@ -81,7 +81,37 @@ def build_parser():
     p.add_argument("--i-max", type=int, default=None)
     p.add_argument("--rtf", action="store_true", help="time each file and write rtfs.csv")
     p.add_argument("--variant", type=str, default="75m", help="flowdec_{75m,25s} architecture of the checkpoint")
+    p.add_argument("--batch-files", type=int, default=1,
+                   help="enhance up to this many files per model call (length-bucketed, flowdec_b200/batching.py); "
+                        "1 = one file per call like the reference")
     return p
+
+
+def flush_batch(model, pending, enhance_kwargs, batch_files, rtf_f):
+    """pending: list of (out_path, y [C,L], sr).  Multi-channel files contribute one clip per channel."""
+    from flowdec_b200.batching import enhance_list
+    if not pending:
+        return
+    clips, owner = [], []
+    for k, (_, y, _) in enumerate(pending):
+        for c in range(y.shape[0]):
+            clips.append(y[c])
+            owner.append((k, c))
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    outs = enhance_list(model, clips, max_batch=batch_files, **enhance_kwargs)
+    end.record()
+    torch.cuda.synchronize()
+    runtime = start.elapsed_time(end) / 1000.0
+    total = sum(y.shape[-1] / sr for _, y, sr in pending)
+    print(f"batch of {len(pending)} files: {runtime:.3f} s for {total:.2f} s of audio -> rtf = {runtime / total:.5f}")
+    for k, (out_path, y, sr) in enumerate(pending):
+        x_hat = torch.stack([outs[j] for j, (kk, _) in enumerate(owner) if kk == k])
+        if rtf_f is not None:       # the batch's runtime is attributed in proportion to duration
+            filetime = y.shape[-1] / sr
+            print(f"{out_path},{runtime * filetime / total:.5f},{filetime:.5f},{runtime / total:.5f}", file=rtf_f)
+        save_wav(out_path, x_hat.cpu(), sr)
+    pending.clear()
 
 
 def main(argv=None):
@@ -117,6 +147,7 @@ def main(argv=None):
     with torch.no_grad(), trf_cm as trf, rtf_cm as rtf_f:
         if rtf_f is not None:
             print("path,runtime,filetime,rtf", file=rtf_f)
+        pending = []
         for i, path in enumerate(noisy):
             if (args.i_min is not None and i < args.i_min) or (args.i_max is not None and i > args.i_max):
                 continue
@@ -131,6 +162,13 @@ def main(argv=None):
                     print("RESAMPLING from", sr, "to", model.sampling_rate)
                     y = torchaudio.functional.resample(y, sr, model.sampling_rate, lowpass_filter_width=64)
                     sr = model.sampling_rate
+                if args.batch_files > 1:
+                    pending.append((out_path, y, sr))
+                    if len(pending) >= 4 * args.batch_files:      # enough clips to fill the length buckets
+                        flush_batch(model, pending, enhance_kwargs, args.batch_files, rtf_f)
+                    if trf is not None:
+                        print(f"{clean[i]} ---> {noisy[i]} ---> {out_path}", file=trf)
+                    continue
                 if args.rtf:
                     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     start.record()
@@ -144,6 +182,7 @@ def main(argv=None):
                 save_wav(out_path, x_hat.cpu(), sr)
             if trf is not None:
                 print(f"{clean[i]} ---> {noisy[i]} ---> {out_path}", file=trf)
+        flush_batch(model, pending, enhance_kwargs, args.batch_files, rtf_f)
 
 
 if __name__ == "__main__":

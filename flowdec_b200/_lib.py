@@ -58,6 +58,9 @@ SIGNATURES = {
     "fd_normfac": [_P, _I, _I, _I, _P, _P],
     "fd_stft1534_compress": [_P, _I, _I, _P, _P, _P, _F, _F, _I, _P, _P],
     "fd_istft1534_decompress": [_P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P],
+    "fd_normfac_ragged": [_P, _I, _I, _P, _I, _P, _P],
+    "fd_stft1534_compress_ragged": [_P, _I, _I, _P, _P, _P, _P, _F, _F, _I, _P, _P],
+    "fd_istft1534_decompress_ragged": [_P, _I, _I, _I, _P, _P, _P, _P, _F, _F, _P, _P],
     "fd_rvq_from_codes": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "fd_dac_conv1d": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "fd_dac_conv_transpose1d": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -18,13 +18,16 @@ constexpr int kBins = 768;
 constexpr int kPad = kNfft / 2;  // 767
 
 // per-sample max |y| -> normfac (<= 1e-8 -> 1, torch.isclose(normfac, 0) with default atol)
-__global__ void __launch_bounds__(1024) normfac_kernel(const float* __restrict__ y, int L, int mode,
+// `lengths` (optional, int32 [B]): per-clip sample counts of a ragged batch stored with row pitch L
+__global__ void __launch_bounds__(1024) normfac_kernel(const float* __restrict__ y, int L,
+                                                        const int* __restrict__ lengths, int mode,
                                                         float* __restrict__ normfac) {
   __shared__ float red[32];
   const int b = blockIdx.x;
+  const int Lb = lengths ? min(lengths[b], L) : L;
   float m = 0.f;
   if (mode == 1)
-    for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, fabsf(y[static_cast<size_t>(b) * L + i]));
+    for (int i = threadIdx.x; i < Lb; i += blockDim.x) m = fmaxf(m, fabsf(y[static_cast<size_t>(b) * L + i]));
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -51,10 +54,11 @@ __global__ void twiddle_kernel(float2* __restrict__ tw) {
 //   grid : (ceil(Tp/32), 768/64, B)
 // out[b][k][m] = beta * |X|^(alpha-1) * X,  X[k,m] = sum_n w[n] ypad[m*hop+n] e^{-2 pi i k n / N}
 __global__ void __launch_bounds__(256) stft_compress_kernel(const float* __restrict__ y, int L,
+                                                            const int* __restrict__ lengths,
                                                             const float* __restrict__ normfac,
                                                             const float* __restrict__ window,
                                                             const float2* __restrict__ tw_g,
-                                                            float alpha, float beta, int frames, int Tp,
+                                                            float alpha, float beta, int frames_all, int Tp,
                                                             float2* __restrict__ out) {
   constexpr int CH = 118;  // samples per smem chunk; 1534 = 13 * 118
   __shared__ float2 tw[kNfft];
@@ -64,6 +68,8 @@ __global__ void __launch_bounds__(256) stft_compress_kernel(const float* __restr
   for (int i = threadIdx.x; i < kNfft; i += 256) tw[i] = tw_g[i];
   const float inv_nf = 1.0f / normfac[b];
   const float* yb = y + static_cast<size_t>(b) * L;
+  const int Lb = lengths ? min(lengths[b], L) : L;       // ragged batch: this clip's own length / frame count
+  const int frames = lengths ? min(1 + Lb / kHop, Tp) : frames_all;
   float re[8], im[8];
   int idx[8];
 #pragma unroll
@@ -80,7 +86,7 @@ __global__ void __launch_bounds__(256) stft_compress_kernel(const float* __restr
       if (m < frames) {
         int p = m * kHop + n0 + nn - kPad;  // index into the unpadded signal
         if (p < 0) p = -p;                  // reflect (no edge repeat)
-        if (p >= L) p = 2 * (L - 1) - p;
+        if (p >= Lb) p = 2 * (Lb - 1) - p;
         v = yb[p] * inv_nf * window[n0 + nn];
       }
       sx[nn][f] = v;
@@ -125,7 +131,8 @@ __global__ void __launch_bounds__(256) stft_compress_kernel(const float* __restr
 //   block = one hop (384 output samples) of one clip; the <= 4 frames overlapping it are
 //   decompressed into smem, every thread accumulates its sample over frames x bins.
 __global__ void __launch_bounds__(384) istft_decompress_kernel(const float2* __restrict__ X, int Tp,
-                                                               int frames,
+                                                               int frames_all,
+                                                               const int* __restrict__ lengths,
                                                                const float* __restrict__ window,
                                                                const float2* __restrict__ tw_g,
                                                                const float* __restrict__ normfac,
@@ -135,6 +142,13 @@ __global__ void __launch_bounds__(384) istft_decompress_kernel(const float2* __r
   __shared__ float2 sX[4][kBins];
   const int b = blockIdx.y;
   const int hblk = blockIdx.x;  // output samples [hblk*384, hblk*384+384)
+  const int Lb = lengths ? min(lengths[b], L) : L;
+  const int frames = lengths ? min(1 + Lb / kHop, Tp) : frames_all;
+  if (hblk * kHop >= Lb) {      // ragged batch: this hop lies beyond the clip -> zeros (uniform per block)
+    const int n = hblk * kHop + threadIdx.x;
+    if (n < L) out[static_cast<size_t>(b) * L + n] = 0.f;
+    return;
+  }
   for (int i = threadIdx.x; i < kNfft; i += 384) tw[i] = tw_g[i];
   // padded position p = n + 767 lies in [hblk*384 + 767, ...): frames m with 0 <= p - m*hop < N
   // for the block: m in [m_hi - 3, m_hi], m_hi = floor((hblk*384 + 767 + 383) / 384)
@@ -161,6 +175,10 @@ __global__ void __launch_bounds__(384) istft_decompress_kernel(const float2* __r
   __syncthreads();
   const int n = hblk * kHop + threadIdx.x;
   if (n >= L) return;
+  if (n >= Lb) {
+    out[static_cast<size_t>(b) * L + n] = 0.f;
+    return;
+  }
   const int p = n + kPad;
   float acc = 0.f, env = 0.f;
 #pragma unroll 1
@@ -196,8 +214,15 @@ extern "C" int fd_twiddles1534(void* tw, cudaStream_t stream) {
 }
 
 extern "C" int fd_normfac(const float* y, int B, int L, int mode, float* normfac, cudaStream_t stream) {
-  normfac_kernel<<<B, 1024, 0, stream>>>(y, L, mode, normfac);
+  normfac_kernel<<<B, 1024, 0, stream>>>(y, L, nullptr, mode, normfac);
   return check_launch("fd_normfac");
+}
+
+extern "C" int fd_normfac_ragged(const float* y, int B, int L, const int* lengths, int mode, float* normfac,
+                                 cudaStream_t stream) {
+  FD_REQUIRE(lengths != nullptr, "fd_normfac_ragged: lengths is NULL");
+  normfac_kernel<<<B, 1024, 0, stream>>>(y, L, lengths, mode, normfac);
+  return check_launch("fd_normfac_ragged");
 }
 
 extern "C" int fd_stft1534_compress(const float* y, int B, int L, const float* normfac,
@@ -207,9 +232,22 @@ extern "C" int fd_stft1534_compress(const float* y, int B, int L, const float* n
   const int frames = 1 + L / kHop;
   FD_REQUIRE(Tp >= frames, "fd_stft1534_compress: Tp=%d < frames=%d", Tp, frames);
   dim3 grid((Tp + 31) / 32, kBins / 64, B);
-  stft_compress_kernel<<<grid, 256, 0, stream>>>(y, L, normfac, window, static_cast<const float2*>(tw),
-                                                 alpha, beta, frames, Tp, static_cast<float2*>(out));
+  stft_compress_kernel<<<grid, 256, 0, stream>>>(y, L, nullptr, normfac, window,
+                                                 static_cast<const float2*>(tw), alpha, beta, frames, Tp,
+                                                 static_cast<float2*>(out));
   return check_launch("fd_stft1534_compress");
+}
+
+extern "C" int fd_stft1534_compress_ragged(const float* y, int B, int L, const int* lengths,
+                                           const float* normfac, const float* window, const void* tw,
+                                           float alpha, float beta, int Tp, void* out, cudaStream_t stream) {
+  FD_REQUIRE(lengths != nullptr && L > kPad, "fd_stft1534_compress_ragged: lengths NULL or pitch %d <= %d", L, kPad);
+  FD_REQUIRE(Tp >= 1, "fd_stft1534_compress_ragged: Tp=%d", Tp);
+  dim3 grid((Tp + 31) / 32, kBins / 64, B);
+  stft_compress_kernel<<<grid, 256, 0, stream>>>(y, L, lengths, normfac, window,
+                                                 static_cast<const float2*>(tw), alpha, beta, 0, Tp,
+                                                 static_cast<float2*>(out));
+  return check_launch("fd_stft1534_compress_ragged");
 }
 
 extern "C" int fd_istft1534_decompress(const void* X, int B, int Tp, int L, const float* window,
@@ -218,8 +256,19 @@ extern "C" int fd_istft1534_decompress(const void* X, int B, int Tp, int L, cons
   const int frames = 1 + L / kHop;
   FD_REQUIRE(Tp >= frames, "fd_istft1534_decompress: Tp=%d < frames=%d", Tp, frames);
   dim3 grid((L + kHop - 1) / kHop, B);
-  istft_decompress_kernel<<<grid, 384, 0, stream>>>(static_cast<const float2*>(X), Tp, frames, window,
+  istft_decompress_kernel<<<grid, 384, 0, stream>>>(static_cast<const float2*>(X), Tp, frames, nullptr, window,
                                                     static_cast<const float2*>(tw), normfac, alpha, beta,
                                                     L, out);
   return check_launch("fd_istft1534_decompress");
+}
+
+extern "C" int fd_istft1534_decompress_ragged(const void* X, int B, int Tp, int L, const int* lengths,
+                                              const float* window, const void* tw, const float* normfac,
+                                              float alpha, float beta, float* out, cudaStream_t stream) {
+  FD_REQUIRE(lengths != nullptr && L >= 1, "fd_istft1534_decompress_ragged: lengths NULL or empty pitch");
+  dim3 grid((L + kHop - 1) / kHop, B);
+  istft_decompress_kernel<<<grid, 384, 0, stream>>>(static_cast<const float2*>(X), Tp, 0, lengths, window,
+                                                    static_cast<const float2*>(tw), normfac, alpha, beta,
+                                                    L, out);
+  return check_launch("fd_istft1534_decompress_ragged");
 }

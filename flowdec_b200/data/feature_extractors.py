@@ -76,14 +76,15 @@ class AmplitudeCompressedComplexSTFT(InvertibleFeatureExtractor):
         return 1 + L // 384
 
     # fused entry points used by FlowModel.enhance ------------------------------------------
-    def stft_compress(self, y2d, normfac, out):
+    def stft_compress(self, y2d, normfac, out, lengths=None):
         """y2d fp32 [B,L] (un-normalised), normfac fp32 [B] -> out fp32 [B,768,Tp,2]; frames beyond
-        1+L//384 are zero (= pad_spec 'zero')."""
-        return ops.stft_compress(y2d, normfac, self.complex_stft.window, self.twiddles(), self.alpha, self.beta, out)
+        1+L//384 are zero (= pad_spec 'zero').  `lengths` (int32 [B]): ragged batch, per-clip L."""
+        return ops.stft_compress(y2d, normfac, self.complex_stft.window, self.twiddles(), self.alpha, self.beta, out,
+                                 lengths=lengths)
 
-    def istft_decompress(self, X, L, normfac, out):
+    def istft_decompress(self, X, L, normfac, out, lengths=None):
         return ops.istft_decompress(X, L, self.complex_stft.window, self.twiddles(), normfac, self.alpha,
-                                    self.beta, out)
+                                    self.beta, out, lengths=lengths)
 
     # reference-shaped API ---------------------------------------------------------------------
     def forward(self, x, comp_eps=None, **kwargs):

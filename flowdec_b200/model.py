@@ -123,8 +123,9 @@ class FlowModel(EnhancementModel):
         """All device work of enhance() on static buffers `st` (graph-capturable)."""
         fe, bb = self.feature_extractor, self.backbone
         B, L, Tp = st["B"], st["L"], st["Tp"]
-        ops.normfac(st["y"], 1 if self.normalize_mode == "noisy" else 0, st["nf"])
-        fe.stft_compress(st["y"], st["nf"], st["Y"])
+        lens = st.get("len")          # int32 [B] for ragged (length-bucketed) batches, else None
+        ops.normfac(st["y"], 1 if self.normalize_mode == "noisy" else 0, st["nf"], lengths=lens)
+        fe.stft_compress(st["y"], st["nf"], st["Y"], lengths=lens)
         ops.x0_noise(st["Y"], self._sigma_vec(768), st["eps"], sigma_fac, st["x"][0])
         cur = 0
         traj = [st["x"][0]] if want_traj else None
@@ -157,13 +158,16 @@ class FlowModel(EnhancementModel):
                 keep = torch.empty_like(st["x"][cur])
                 keep.copy_(st["x"][cur])
                 traj.append(keep)
-        fe.istft_decompress(st["x"][cur], L, st["nf"], st["out"])
+        fe.istft_decompress(st["x"][cur], L, st["nf"], st["out"], lengths=lens)
         return traj
 
-    def _static(self, B, L, dev):
-        Tp = padded_frames(1 + L // 384)
+    def _static(self, B, L, dev, Tp=None):
+        ragged = Tp is not None       # ragged bucket: rows of pitch L = Tp*384 hold clips of individual lengths
+        if Tp is None:
+            Tp = padded_frames(1 + L // 384)
         f32 = dict(device=dev, dtype=torch.float32)
-        return dict(B=B, L=L, Tp=Tp, y=torch.empty(B, L, **f32), nf=torch.empty(B, **f32),
+        extra = dict(len=torch.empty(B, device=dev, dtype=torch.int32)) if ragged else {}
+        return dict(B=B, L=L, Tp=Tp, y=torch.empty(B, L, **f32), nf=torch.empty(B, **f32), **extra,
                     Y=torch.empty(B, 768, Tp, 2, **f32), eps=torch.empty(B, 768, Tp, 2, **f32),
                     x=[torch.empty(B, 768, Tp, 2, **f32) for _ in range(2)],
                     tmp=torch.empty(B, 768, Tp, 2, **f32), out=torch.empty(B, L, **f32))
@@ -171,14 +175,20 @@ class FlowModel(EnhancementModel):
     @torch.no_grad()
     def enhance(self, y, return_preprocess_info: bool = False, N: int = 50, solver: str = "euler",
                 with_grad: bool = False, sigma_fac: float = 1.0, return_traj: bool = False,
-                noise: Optional[torch.Tensor] = None, **kwargs):
+                noise: Optional[torch.Tensor] = None, lengths=None, **kwargs):
         """Enhance a coded waveform `y` ([B,1,L], [1,L] or [L]); reference model.py:476-528.
 
         Extra keyword `noise`: complex64 [B,1,768,Tp] standing in for torch.randn_like(Y) (parity
-        tests inject the oracle's draw).  Unknown kwargs (predictor/corrector/snr from the
-        reference CLI, enhance.py:55-61) are accepted and ignored like the reference does."""
+        tests inject the oracle's draw).  Extra keyword `lengths` (B ints): `y` is a zero-padded ragged
+        batch and clip b has lengths[b] valid samples; all clips must fall into the same padded-frame
+        bucket (64*ceil((1 + L_b//384)/64)), and each then gets exactly the computation it would get alone
+        (own normfac, frames, reflect padding and istft length; samples beyond L_b come back as 0) — see
+        flowdec_b200/batching.py.  Unknown kwargs (predictor/corrector/snr from the reference CLI,
+        enhance.py:55-61) are accepted and ignored like the reference does."""
         if with_grad:
             raise NotImplementedError("with_grad=True (backprop through the solver) is a training feature")
+        if lengths is not None:
+            return self._enhance_ragged(y, lengths, N, solver, sigma_fac, noise, return_preprocess_info, return_traj)
         solver = get_solver(solver)
         dev = self.device
         if dev.type != "cuda":
@@ -240,6 +250,71 @@ class FlowModel(EnhancementModel):
             x_hat = x_hat.squeeze(0)
         x_hat = x_hat.to(y_in.device)
         return (x_hat, info) if return_preprocess_info else x_hat
+
+
+    def _enhance_ragged(self, y, lengths, N, solver, sigma_fac, noise, return_preprocess_info, return_traj):
+        """length-bucketed batch: see enhance(lengths=)"""
+        if return_traj:
+            raise NotImplementedError("return_traj is not available for ragged batches")
+        solver = get_solver(solver)
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("flowdec_b200 runs on CUDA (sm_100a) only; call model.cuda()")
+        if y.ndim == 2:
+            y = y.unsqueeze(1)
+        if y.ndim != 3 or y.shape[1] != 1:
+            raise ValueError(f"ragged batches are [B,1,Lmax] (or [B,Lmax]), got {tuple(y.shape)}")
+        lens = [int(v) for v in (lengths.tolist() if torch.is_tensor(lengths) else lengths)]
+        B, Lin = y.shape[0], y.shape[2]
+        if len(lens) != B:
+            raise ValueError(f"{len(lens)} lengths for a batch of {B}")
+        if min(lens) <= 767 or max(lens) > Lin:
+            raise ValueError(f"clip lengths must be in (767, {Lin}], got min {min(lens)} max {max(lens)}")
+        buckets = {padded_frames(1 + n // 384) for n in lens}
+        if len(buckets) != 1:
+            raise ValueError(f"clips of one ragged batch must share the padded-frame bucket, got {sorted(buckets)}; "
+                             "use flowdec_b200.batching.enhance_list to bucket a list of clips")
+        Tp = buckets.pop()
+        pitch = Tp * 384
+        key = ("ragged", B, Tp, int(N), solver, float(sigma_fac))
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = dict(st=self._static(B, pitch, dev, Tp=Tp), graph=None, warm=0)
+            self._graphs[key] = entry
+        st = entry["st"]
+        n_copy = min(Lin, pitch)
+        if n_copy < pitch:
+            st["y"][:, n_copy:].zero_()
+        st["y"][:, :n_copy].copy_(y.reshape(B, Lin)[:, :n_copy], non_blocking=True)
+        st["len"].copy_(torch.tensor(lens, dtype=torch.int32), non_blocking=True)
+        if noise is None:
+            eps = torch.randn(B, 1, 768, Tp, dtype=torch.complex64, device=dev)
+        else:
+            eps = noise.to(dev, torch.complex64)
+        st["eps"].copy_(torch.view_as_real(eps.reshape(B, 768, Tp)))
+        if not self.use_cuda_graph:
+            self._run(st, N, solver, sigma_fac, False)
+        elif entry["graph"] is None:
+            if entry["warm"] == 0:
+                self._run(st, N, solver, sigma_fac, False)
+                entry["warm"] = 1
+            else:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._run(st, N, solver, sigma_fac, False)
+                entry["graph"] = g
+                g.replay()
+        else:
+            entry["graph"].replay()
+        Lmax = max(lens)
+        x_hat = st["out"][:, :Lmax].clone().reshape(B, 1, Lmax).to(y.device)
+        if not return_preprocess_info:
+            return x_hat
+        info = dict(orig_length=lens, normfac=st["nf"].clone().reshape(B, 1, 1),
+                    undo_pad_fn=(lambda Y_, T=[1 + n // 384 for n in lens]: [Y_[i, ..., :t] for i, t in enumerate(T)]),
+                    squeeze_dims=0)
+        return x_hat, info
 
 
 class ScoreModel(EnhancementModel):

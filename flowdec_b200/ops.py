@@ -239,28 +239,45 @@ def twiddles1534(device):
     return tw
 
 
-def normfac(y2d, mode, out):
+def normfac(y2d, mode, out, lengths=None):
+    """lengths (int32 [B], device) selects the ragged form: row b holds lengths[b] <= L valid samples"""
     B, L = y2d.shape
-    _lib.check(_lib.lib().fd_normfac(_lib.ptr(y2d), B, L, int(mode), _lib.ptr(out), _lib.stream_ptr()),
-               "fd_normfac")
+    if lengths is None:
+        _lib.check(_lib.lib().fd_normfac(_lib.ptr(y2d), B, L, int(mode), _lib.ptr(out), _lib.stream_ptr()),
+                   "fd_normfac")
+    else:
+        _lib.check(_lib.lib().fd_normfac_ragged(_lib.ptr(y2d), B, L, _lib.ptr(lengths), int(mode), _lib.ptr(out),
+                                                _lib.stream_ptr()), "fd_normfac_ragged")
     return out
 
 
-def stft_compress(y2d, nf, window, tw, alpha, beta, out):
+def stft_compress(y2d, nf, window, tw, alpha, beta, out, lengths=None):
     """y2d fp32 [B,L]; out float2 [B,768,Tp] (as fp32 [B,768,Tp,2])."""
     B, L = y2d.shape
     Tp = out.shape[2]
-    rc = _lib.lib().fd_stft1534_compress(_lib.ptr(y2d), B, L, _lib.ptr(nf), _lib.ptr(window), _lib.ptr(tw),
-                                         ctypes.c_float(alpha), ctypes.c_float(beta), Tp, _lib.ptr(out),
-                                         _lib.stream_ptr())
-    _lib.check(rc, "fd_stft1534_compress")
+    if lengths is None:
+        rc = _lib.lib().fd_stft1534_compress(_lib.ptr(y2d), B, L, _lib.ptr(nf), _lib.ptr(window), _lib.ptr(tw),
+                                             ctypes.c_float(alpha), ctypes.c_float(beta), Tp, _lib.ptr(out),
+                                             _lib.stream_ptr())
+        _lib.check(rc, "fd_stft1534_compress")
+    else:
+        rc = _lib.lib().fd_stft1534_compress_ragged(_lib.ptr(y2d), B, L, _lib.ptr(lengths), _lib.ptr(nf),
+                                                    _lib.ptr(window), _lib.ptr(tw), ctypes.c_float(alpha),
+                                                    ctypes.c_float(beta), Tp, _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(rc, "fd_stft1534_compress_ragged")
     return out
 
 
-def istft_decompress(X, L, window, tw, nf, alpha, beta, out):
+def istft_decompress(X, L, window, tw, nf, alpha, beta, out, lengths=None):
     B, Tp = X.shape[0], X.shape[2]
-    rc = _lib.lib().fd_istft1534_decompress(_lib.ptr(X), B, Tp, L, _lib.ptr(window), _lib.ptr(tw), _lib.ptr(nf),
-                                            ctypes.c_float(alpha), ctypes.c_float(beta), _lib.ptr(out),
-                                            _lib.stream_ptr())
-    _lib.check(rc, "fd_istft1534_decompress")
+    if lengths is None:
+        rc = _lib.lib().fd_istft1534_decompress(_lib.ptr(X), B, Tp, L, _lib.ptr(window), _lib.ptr(tw), _lib.ptr(nf),
+                                                ctypes.c_float(alpha), ctypes.c_float(beta), _lib.ptr(out),
+                                                _lib.stream_ptr())
+        _lib.check(rc, "fd_istft1534_decompress")
+    else:
+        rc = _lib.lib().fd_istft1534_decompress_ragged(_lib.ptr(X), B, Tp, L, _lib.ptr(lengths), _lib.ptr(window),
+                                                       _lib.ptr(tw), _lib.ptr(nf), ctypes.c_float(alpha),
+                                                       ctypes.c_float(beta), _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(rc, "fd_istft1534_decompress_ragged")
     return out

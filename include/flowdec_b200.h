@@ -132,6 +132,18 @@ int fd_stft1534_compress(const float* y, int B, int L, const float* normfac, con
 /* inverse: decompress, overlap-add iSTFT (torch.istft semantics incl. length=L), times normfac */
 int fd_istft1534_decompress(const void* X, int B, int Tp, int L, const float* window, const void* tw,
                             const float* normfac, float alpha, float beta, float* out, fd_stream_t stream);
+/* ragged batches (length-bucketed batching across files): rows of pitch L hold clips of
+ * lengths[b] <= L samples (int32 [B], device; every lengths[b] > 767 and 1 + lengths[b]/384 <= Tp, checked by
+ * the caller).  Each clip gets exactly the frames, reflect padding, normalisation and istft(length=) it would
+ * get when processed alone (enhance.py:113-131 runs one file at a time); samples / frames beyond a clip are 0. */
+int fd_normfac_ragged(const float* y, int B, int L, const int* lengths, int mode, float* normfac,
+                      fd_stream_t stream);
+int fd_stft1534_compress_ragged(const float* y, int B, int L, const int* lengths, const float* normfac,
+                                const float* window, const void* tw, float alpha, float beta, int Tp, void* out,
+                                fd_stream_t stream);
+int fd_istft1534_decompress_ragged(const void* X, int B, int Tp, int L, const int* lengths, const float* window,
+                                   const void* tw, const float* normfac, float alpha, float beta, float* out,
+                                   fd_stream_t stream);
 
 /* ---- upstream NDAC (descript-audio-codec 1.0.0; call sites demo.ipynb:101-105) ----------------
  * layout [B, C, T] fp32 as upstream; weight-norm already folded into w. */

@@ -147,3 +147,43 @@ def test_long_and_ragged_clips(model):
     assert out.shape == y.shape and torch.isfinite(out).all()
     one = model.enhance(y[2:3], N=1, solver="euler", noise=eps[2:3])
     assert torch.equal(one, out[2:3])
+
+
+def test_ragged_batch_matches_single_clips(model):
+    """length-bucketed batching across files: clips of different lengths inside one
+    padded-frame bucket share a batch, and each comes out bit-identical to enhancing it alone"""
+    from flowdec_b200.batching import enhance_list, frames_bucket
+    from flowdec_b200.util.synth import synth_waveforms
+    lens = [48000, 45001, 41233, 48383, 24960 + 767]          # frames 126, 118, 108, 126, 67 -> Tp 128
+    assert {frames_bucket(n) for n in lens} == {128}
+    waves = [synth_waveforms(1, n, seed=100 + i)[0, 0] for i, n in enumerate(lens)]
+    g = torch.Generator().manual_seed(5)
+    eps = torch.randn(len(lens), 1, 768, 128, dtype=torch.complex64, generator=g)
+    y = torch.zeros(len(lens), 1, max(lens))
+    for i, w in enumerate(waves):
+        y[i, 0, :lens[i]] = w
+    out, info = model.enhance(y, N=1, solver="midpoint", noise=eps, lengths=lens, return_preprocess_info=True)
+    assert out.shape == (len(lens), 1, max(lens)) and torch.isfinite(out).all()
+    assert info["orig_length"] == lens
+    for i, n in enumerate(lens):
+        alone, info1 = model.enhance(waves[i].reshape(1, 1, n), N=1, solver="midpoint", noise=eps[i:i + 1],
+                                     return_preprocess_info=True)
+        assert torch.equal(out[i, :, :n], alone[0]), f"clip {i} (L={n}) differs from its single-clip result"
+        assert (out[i, :, n:] == 0).all()
+        assert torch.equal(info["normfac"][i].cpu(), info1["normfac"][0].cpu())
+    # second call replays the captured graph with other lengths of the same bucket
+    lens2 = [47000, 48000, 30000, 46001, 44444]
+    y2 = torch.zeros(len(lens2), 1, 48000)
+    for i, n in enumerate(lens2):
+        y2[i, 0, :n] = waves[i][:n] if n <= lens[i] else synth_waveforms(1, n, seed=200 + i)[0, 0]
+    for _ in range(2):
+        out2 = model.enhance(y2, N=1, solver="midpoint", noise=eps, lengths=lens2)
+    alone = model.enhance(y2[2:3, :, :30000], N=1, solver="midpoint", noise=eps[2:3])
+    assert torch.equal(out2[2, :, :30000], alone[0])
+    # mixed buckets are rejected by enhance(lengths=) and handled by enhance_list
+    with pytest.raises(ValueError):
+        model.enhance(torch.zeros(2, 1, 96000), N=1, lengths=[96000, 48000])
+    clips = [waves[0], synth_waveforms(1, 96000, seed=300)[0, 0], waves[2].reshape(1, -1), waves[4]]
+    outs = enhance_list(model, clips, max_batch=2, N=1, solver="euler")
+    assert [o.shape for o in outs] == [c.shape for c in clips]
+    assert all(torch.isfinite(o).all() for o in outs)

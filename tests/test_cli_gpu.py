@@ -29,3 +29,12 @@ def test_enhance_cli_roundtrip(tmp_path):
         assert sr == 48000 and np.isfinite(d).all() and d.shape[0] >= 23990
     lines = open(outdir / "rtfs.csv").read().strip().splitlines()
     assert lines[0] == "path,runtime,filetime,rtf" and len(lines) == 3
+    # length-bucketed batching across files: same outputs' shapes, one rtf line per file
+    out2 = tmp_path / "out_batched"
+    wavfile.write(indir / "c.wav", 48000, synth_waveforms(1, 30000, seed=6)[0, 0].numpy())
+    cli.main(["--ckpt", str(ckpt), "--files", str(indir), "--outdir", str(out2), "--N", "1", "--solver", "euler",
+              "--rtf", "--batch-files", "2"])
+    for name, n in (("a.wav", 24000), ("b.wav", 23990), ("c.wav", 30000)):
+        sr, d = wavfile.read(out2 / name)
+        assert sr == 48000 and np.isfinite(d).all() and d.shape[0] >= n
+    assert len(open(out2 / "rtfs.csv").read().strip().splitlines()) == 4

@@ -89,3 +89,23 @@ def test_unsupported_configs_fail_loudly():
     m = build_flowdec("75m")
     with pytest.raises(RuntimeError):  # CPU model: there is no CPU fallback
         m.enhance(torch.zeros(1, 1, 24000), N=1)
+
+
+def test_length_bucketed_batching_host_logic():
+    """flowdec_b200/batching.py: buckets = padded STFT frame counts (pad_spec, util/other.py:25-52)"""
+    import torch
+    from flowdec_b200.batching import bucket_by_frames, frames_bucket, pad_batch
+    assert [frames_bucket(n) for n in (768, 24191, 24192, 48000, 96000, 192000)] == [64, 64, 64, 128, 256, 512]
+    assert frames_bucket(64 * 384 - 1) == 64 and frames_bucket(64 * 384) == 128
+    lens = [96000, 48000, 95000, 100000, 24960, 96001, 97000]
+    batches = bucket_by_frames(lens, 2)
+    assert batches == [[3], [0, 2], [5, 6], [1, 4]]
+    assert sorted(i for b in batches for i in b) == list(range(len(lens)))
+    for b in batches:
+        assert len({frames_bucket(lens[i]) for i in b}) == 1 and len(b) <= 2
+    with pytest.raises(ValueError):
+        bucket_by_frames([96000, 767], 4)
+    with pytest.raises(ValueError):
+        bucket_by_frames([96000], 0)
+    y, l = pad_batch([torch.arange(5.0), torch.ones(1, 3)])
+    assert y.shape == (2, 1, 5) and l == [5, 3] and y[1, 0].tolist() == [1, 1, 1, 0, 0]
