@@ -50,9 +50,12 @@ __global__ void twiddle_kernel(float2* __restrict__ tw) {
 }
 
 // STFT + amplitude compression + zero padding of the frame axis.
-//   block: 32 frames (lanes) x 8 bin-groups (warps), 8 bins per thread -> 64 bins per block
-//   grid : (ceil(Tp/32), 768/64, B)
+//   block: 128 frames (4 per lane: lane + 32 f) x 8 bin-groups (warps), 8 bins per thread -> 64 bins per block;
+//          one twiddle fetch (warp-uniform address -> broadcast) feeds 4 frames
+//   grid : (ceil(Tp/128), 768/64, B)
 // out[b][k][m] = beta * |X|^(alpha-1) * X,  X[k,m] = sum_n w[n] ypad[m*hop+n] e^{-2 pi i k n / N}
+constexpr int kStftFpt = 4;                 // frames per thread
+constexpr int kStftFrames = 32 * kStftFpt;  // frames per block
 __global__ void __launch_bounds__(256) stft_compress_kernel(const float* __restrict__ y, int L,
                                                             const int* __restrict__ lengths,
                                                             const float* __restrict__ normfac,
@@ -60,26 +63,27 @@ __global__ void __launch_bounds__(256) stft_compress_kernel(const float* __restr
                                                             const float2* __restrict__ tw_g,
                                                             float alpha, float beta, int frames_all, int Tp,
                                                             float2* __restrict__ out) {
-  constexpr int CH = 118;  // samples per smem chunk; 1534 = 13 * 118
+  constexpr int CH = 59;  // samples per smem chunk; 1534 = 26 * 59
   __shared__ float2 tw[kNfft];
-  __shared__ float sx[CH][33];
+  __shared__ float sx[CH][kStftFrames + 1];
   const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
-  const int m0 = blockIdx.x * 32, k0 = blockIdx.y * 64 + wg * 8, b = blockIdx.z;
+  const int m0 = blockIdx.x * kStftFrames, k0 = blockIdx.y * 64 + wg * 8, b = blockIdx.z;
   for (int i = threadIdx.x; i < kNfft; i += 256) tw[i] = tw_g[i];
   const float inv_nf = 1.0f / normfac[b];
   const float* yb = y + static_cast<size_t>(b) * L;
   const int Lb = lengths ? min(lengths[b], L) : L;       // ragged batch: this clip's own length / frame count
   const int frames = lengths ? min(1 + Lb / kHop, Tp) : frames_all;
-  float re[8], im[8];
+  float re[kStftFpt][8], im[kStftFpt][8];
   int idx[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    re[j] = im[j] = 0.f;
     idx[j] = 0;
+#pragma unroll
+    for (int f = 0; f < kStftFpt; ++f) re[f][j] = im[f][j] = 0.f;
   }
   for (int n0 = 0; n0 < kNfft; n0 += CH) {
     __syncthreads();
-    for (int i = threadIdx.x; i < CH * 32; i += 256) {
+    for (int i = threadIdx.x; i < CH * kStftFrames; i += 256) {
       const int nn = i % CH, f = i / CH;
       const int m = m0 + f;
       float v = 0.f;
@@ -92,34 +96,36 @@ __global__ void __launch_bounds__(256) stft_compress_kernel(const float* __restr
       sx[nn][f] = v;
     }
     __syncthreads();
-    // idx[j] = (k_j * n0) mod N at chunk start
-    if (n0 == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) idx[j] = 0;
-    }
 #pragma unroll 2
     for (int nn = 0; nn < CH; ++nn) {
-      const float s = sx[nn][lane];
+      float sv[kStftFpt];
+#pragma unroll
+      for (int f = 0; f < kStftFpt; ++f) sv[f] = sx[nn][lane + 32 * f];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float2 t = tw[idx[j]];
-        re[j] = fmaf(s, t.x, re[j]);
-        im[j] = fmaf(-s, t.y, im[j]);
+        const float2 t = tw[idx[j]];        // (k_j * n) mod N, same for the whole warp
+#pragma unroll
+        for (int f = 0; f < kStftFpt; ++f) {
+          re[f][j] = fmaf(sv[f], t.x, re[f][j]);
+          im[f][j] = fmaf(-sv[f], t.y, im[f][j]);
+        }
         idx[j] += k0 + j;
         if (idx[j] >= kNfft) idx[j] -= kNfft;
       }
     }
   }
-  const int m = m0 + lane;
-  if (m < Tp) {
+#pragma unroll
+  for (int f = 0; f < kStftFpt; ++f) {
+    const int m = m0 + lane + 32 * f;
+    if (m >= Tp) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float2 o = make_float2(0.f, 0.f);
       if (m < frames) {
-        const float mag = sqrtf(re[j] * re[j] + im[j] * im[j]);
+        const float mag = sqrtf(re[f][j] * re[f][j] + im[f][j] * im[f][j]);
         if (mag > 0.f) {
           const float sc = beta * powf(mag, alpha - 1.0f);
-          o = make_float2(re[j] * sc, im[j] * sc);
+          o = make_float2(re[f][j] * sc, im[f][j] * sc);
         }
       }
       out[(static_cast<size_t>(b) * kBins + (k0 + j)) * Tp + m] = o;
@@ -188,17 +194,31 @@ __global__ void __launch_bounds__(384) istft_decompress_kernel(const float2* __r
     if (m < 0 || m >= frames || j < 0 || j >= kNfft) continue;
     const float wj = window[j];
     env = fmaf(wj, wj, env);
-    float s = 0.f;
+    // sum_k Re(X_k e^{+2 pi i j k / N}): the phasor advances by e^{2 pi i j / N} per bin; it is advanced by a
+    // complex multiply and re-seeded from the table every 16 bins (fp32 drift <= ~1e-6), which replaces a
+    // per-bin table lookup whose addresses (j*k mod N, j = lane-dependent) collide in the shared-memory banks
+    const float2 rot = tw[j];
+    const int inc16 = (16 * j) % kNfft;
+    float s0 = 0.f, s1 = 0.f;
     int idx = 0;
-#pragma unroll 4
-    for (int k = 0; k < kBins; ++k) {
-      const float2 x = sX[fi][k];
-      const float2 t = tw[idx];
-      s = fmaf(x.x, t.x, s);
-      s = fmaf(-x.y, t.y, s);
-      idx += j;
+#pragma unroll 1
+    for (int kb = 0; kb < kBins; kb += 16) {
+      float2 ph = tw[idx];
+#pragma unroll
+      for (int kk = 0; kk < 16; kk += 2) {
+        const float2 x0 = sX[fi][kb + kk];
+        s0 = fmaf(x0.x, ph.x, s0);
+        s0 = fmaf(-x0.y, ph.y, s0);
+        const float2 p1 = make_float2(fmaf(ph.x, rot.x, -ph.y * rot.y), fmaf(ph.x, rot.y, ph.y * rot.x));
+        const float2 x1 = sX[fi][kb + kk + 1];
+        s1 = fmaf(x1.x, p1.x, s1);
+        s1 = fmaf(-x1.y, p1.y, s1);
+        ph = make_float2(fmaf(p1.x, rot.x, -p1.y * rot.y), fmaf(p1.x, rot.y, p1.y * rot.x));
+      }
+      idx += inc16;
       if (idx >= kNfft) idx -= kNfft;
     }
+    const float s = s0 + s1;
     acc = fmaf(wj, s * (1.0f / kNfft), acc);
   }
   out[static_cast<size_t>(b) * L + n] = (env > 1e-11f ? acc / env : 0.f) * normfac[b];
@@ -231,7 +251,7 @@ extern "C" int fd_stft1534_compress(const float* y, int B, int L, const float* n
   FD_REQUIRE(L > kPad, "fd_stft1534_compress: L=%d must exceed the reflect pad %d", L, kPad);
   const int frames = 1 + L / kHop;
   FD_REQUIRE(Tp >= frames, "fd_stft1534_compress: Tp=%d < frames=%d", Tp, frames);
-  dim3 grid((Tp + 31) / 32, kBins / 64, B);
+  dim3 grid((Tp + kStftFrames - 1) / kStftFrames, kBins / 64, B);
   stft_compress_kernel<<<grid, 256, 0, stream>>>(y, L, nullptr, normfac, window,
                                                  static_cast<const float2*>(tw), alpha, beta, frames, Tp,
                                                  static_cast<float2*>(out));
@@ -243,7 +263,7 @@ extern "C" int fd_stft1534_compress_ragged(const float* y, int B, int L, const i
                                            float alpha, float beta, int Tp, void* out, cudaStream_t stream) {
   FD_REQUIRE(lengths != nullptr && L > kPad, "fd_stft1534_compress_ragged: lengths NULL or pitch %d <= %d", L, kPad);
   FD_REQUIRE(Tp >= 1, "fd_stft1534_compress_ragged: Tp=%d", Tp);
-  dim3 grid((Tp + 31) / 32, kBins / 64, B);
+  dim3 grid((Tp + kStftFrames - 1) / kStftFrames, kBins / 64, B);
   stft_compress_kernel<<<grid, 256, 0, stream>>>(y, L, lengths, normfac, window,
                                                  static_cast<const float2*>(tw), alpha, beta, 0, Tp,
                                                  static_cast<float2*>(out));

@@ -184,7 +184,8 @@ def test_time_embedding_matvec():
         assert rel_l2(te.cpu(), ref) < 2e-5, (t, rel_l2(te.cpu(), ref))
 
 
-@pytest.mark.parametrize("L,kind", [(24000, "tones"), (48000, "gauss"), (30011, "tones"), (768, "gauss"), (24000, "zeros")])
+@pytest.mark.parametrize("L,kind", [(24000, "tones"), (48000, "gauss"), (30011, "tones"), (768, "gauss"), (24000, "zeros"),
+                                    (96000, "tones"), (61001, "gauss")])
 def test_stft_istft_vs_oracle(L, kind):
     B = 2
     y = synth_waveforms(B, L, seed=99, kind=kind)
