@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libflowdec_b200.so")
+_LIB_PATH = os.environ.get("FD_LIB_PATH") or os.path.join(_HERE, "libflowdec_b200.so")   # FD_LIB_PATH: A/B builds
 _lib = None
 
 

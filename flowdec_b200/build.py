@@ -32,18 +32,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defs=(), lib_out=None):
+    """defs / lib_out: extra -D flags and an alternative output path (A/B variants for tools/bench_variants.py)"""
+    if lib_out is None and not defs and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if lib_out is None else "build_" + os.path.basename(lib_out).replace(".", "_"))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-I", CSRC, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *defs, "-I", CSRC, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, pr in procs:
@@ -56,9 +57,9 @@ def build(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_out or LIB, *objs, "-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib_out or LIB
 
 
 if __name__ == "__main__":

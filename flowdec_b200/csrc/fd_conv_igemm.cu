@@ -404,6 +404,7 @@ struct HaloParams {
   const float* bias;
   float* stats;
   long long* dbg;                // optional [16] cycle counters written by block 0 (tools/halo_dbg.py)
+  int xf_mode;                   // experiments (env FD_HALO_XF_MODE): 0 normal, 1 barriers only, 2 loads only, 3 no stores
 };
 
 template <int N>
@@ -418,8 +419,17 @@ struct HaloCfg {
                                     kSsFloats * 4 + 512;
 };
 
+// Transform-warp placement.  FD_XF_LAYOUT 0 (default): warps 7..14 (two of them share the MMA warp's scheduler
+// partition, warp % 4 == 1); 1: warps {7,8,10,11,12,14,15,16}, i.e. none on that partition.  Measured identical
+// on B200 (309.0 us both, 384x128 256->256 x 8 clips; whole step 113.5 vs 113.2 audio-s/s), so the MMA issue
+// is not what the transform's ALU work slows down — kept as a build-time switch for tools/bench_variants.py.
+#ifndef FD_XF_LAYOUT
+#define FD_XF_LAYOUT 0
+#endif
+constexpr int kHaloXfThreads = FD_XF_LAYOUT ? 544 : 480;
+
 template <int N, bool XF>
-__global__ void __launch_bounds__(XF ? 480 : 224, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   using Cfg = HaloCfg<N>;
   constexpr int SA = Cfg::kStagesA, SB = Cfg::kStagesB, B_BYTES = Cfg::kBBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -645,9 +655,10 @@ __global__ void __launch_bounds__(XF ? 480 : 224, 1) conv_halo_kernel(const __gr
       if (acc == 0) acc_phase ^= 1u;
     }
     if (leader) tma_store_wait_all<0>();
-  } else if (XF && warp >= 7) {
-    // ---------------------------------------------------------------- transform warps (7..14)
-    const int tx = threadIdx.x - 224;       // 0..255
+  } else if (XF && warp >= 7 && !(FD_XF_LAYOUT && (warp & 3) == 1)) {
+    // ---------------------------------------------------------------- transform warps (8 of them)
+    const int tq = FD_XF_LAYOUT ? (warp - 7 - (warp > 9 ? 1 : 0) - (warp > 13 ? 1 : 0)) : (warp - 7);
+    const int tx = tq * 32 + lane;          // 0..255
     const int j = tx & 7;                   // logical 16-byte chunk = channels j*8 .. j*8+7 of the slice
     const int g = tx >> 3;                  // rows r = g + 32*i  (r & 7 == g & 7 for all of them)
     const int slot = (j ^ (g & 7)) << 4;    // physical chunk position inside the 128-byte row
@@ -678,7 +689,7 @@ __global__ void __launch_bounds__(XF ? 480 : 224, 1) conv_halo_kernel(const __gr
           if (p.dbg) xq = clock64();
           mbar_wait(&fullA[sa], pa);
           if (p.dbg) { const long long now = clock64(); x_wait += now - xq; xq = now; }
-          if (xf) {
+          if (xf && p.xf_mode != 1) {
             float sc[8], sh[8];
             const uint32_t ss_addr = smem_u32(sSS) + static_cast<uint32_t>(p.seg_ss_off[s] + ks * kSliceK + j * 8) * 8u;
 #pragma unroll
@@ -702,6 +713,12 @@ __global__ void __launch_bounds__(XF ? 480 : 224, 1) conv_halo_kernel(const __gr
             }
             if (p.dbg) { const long long now = clock64(); x_ld += now - xq; }
             // phase 2: affine + SiLU (one MUFU op per element) and store back; out-of-image rows -> 0
+            if (p.xf_mode == 2) {
+              uint32_t acc_x = 0;
+#pragma unroll
+              for (int i = 0; i < kItems; ++i) acc_x ^= raw[i].x ^ raw[i].y ^ raw[i].z ^ raw[i].w;
+              if (acc_x == 0x12345678u) sts128(base, raw[0]);      // keep the loads alive
+            } else
 #pragma unroll
             for (int i = 0; i < kItems; ++i) {
               const int r = g + 32 * i;
@@ -715,7 +732,7 @@ __global__ void __launch_bounds__(XF ? 480 : 224, 1) conv_halo_kernel(const __gr
                   q.z = pack_bf16x2(silu_fast(fmaf(a2.x, sc[4], sh[4])), silu_fast(fmaf(a2.y, sc[5], sh[5])));
                   q.w = pack_bf16x2(silu_fast(fmaf(a3.x, sc[6], sh[6])), silu_fast(fmaf(a3.y, sc[7], sh[7])));
                 }
-                sts128(base + static_cast<uint32_t>(r) * 128u, q);
+                if (p.xf_mode != 3 || q.x == 0x12345678u) sts128(base + static_cast<uint32_t>(r) * 128u, q);
               }
             }
             long long f0 = 0;
@@ -858,7 +875,7 @@ static int launch_halo(const HaloParams& p, int max_ctas, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(XF ? 480 : 224);
+  cfg.blockDim = dim3(XF ? kHaloXfThreads : 224);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -960,6 +977,8 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
       {
         const char* e = getenv("FD_HALO_DBG");   // device pointer (decimal) of an int64[16] buffer
         hp.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr;
+        const char* m = getenv("FD_HALO_XF_MODE");
+        hp.xf_mode = m ? atoi(m) : 0;
       }
       if (npad == 256) return any_xf ? launch_halo<256, true>(hp, max_ctas, stream)
                                      : launch_halo<256, false>(hp, max_ctas, stream);

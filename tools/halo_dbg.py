@@ -15,9 +15,13 @@ b = torch.randn(C, device="cuda")
 wp = pack_conv_weight([(w, 9)], npad=C)
 out = torch.empty(B, H, W, C, device="cuda", dtype=torch.bfloat16)
 ss = torch.ones(B, C, 2, device="cuda")
-for name, srcs, halo in [("per-tap pair kernel", [(x, 0, C, 9)], False), ("halo raw", [(x, 0, C, 9)], True),
-                         ("halo fused GN+SiLU", [(x, 0, C, 9, ss, 0)], True)]:
+for name, srcs, halo, mode in [("per-tap pair kernel", [(x, 0, C, 9)], False, 0), ("halo raw", [(x, 0, C, 9)], True, 0),
+                               ("halo fused GN+SiLU", [(x, 0, C, 9, ss, 0)], True, 0),
+                               ("  fused, barriers only", [(x, 0, C, 9, ss, 0)], True, 1),
+                               ("  fused, loads only", [(x, 0, C, 9, ss, 0)], True, 2),
+                               ("  fused, no stores", [(x, 0, C, 9, ss, 0)], True, 3)]:
     ops.HALO_TILES = halo
+    os.environ["FD_HALO_XF_MODE"] = str(mode)
     for _ in range(3):
         conv_igemm(srcs, wp, b, out)
     torch.cuda.synchronize()
