@@ -203,7 +203,7 @@ def workload_config(args):
             "per_gpu_batch": args.batch, "clip_seconds": args.seconds, "nfe": nfe_of(args.N, args.solver),
             "solver": args.solver, "sharding": f"dp{args.gpus} (clip batch, no data-path collective)",
             "l2": "working set (multi-GB activations per micro-batch) >> 126 MB L2; no explicit flush",
-            "micro_batch": "clips per backbone pass and concurrent CUDA streams: see model.max_batch / overlap_streams"}
+            "micro_batch": "16 clips (<= 4096 padded frames) per backbone pass, 2 passes in flight on separate CUDA streams (model.max_batch / overlap_streams)"}
 
 
 # ------------------------------------------------------------------------------------------------

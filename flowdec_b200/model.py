@@ -71,7 +71,7 @@ class FlowModel(EnhancementModel):
         self.sigma_y = nn.Parameter(as_t(sigma_y), requires_grad=False)
         self._graphs = {}
         self.use_cuda_graph = True
-        self.max_batch = 8          # clips per backbone pass (micro-batch)
+        self.max_batch = 16         # clips per backbone pass (micro-batch); 16 x 2 s = 8 x 4 s = 4096 frames
         self.max_frames_per_pass = 4096   # padded STFT frames per backbone pass (8 clips x 4 s)
         self.overlap_streams = 2    # micro-batches in flight on separate CUDA streams
         self._streams = []

@@ -128,7 +128,7 @@ def test_batch_independence_and_microbatching(model):
     model.max_batch = 2
     model._graphs = {}
     split = model.enhance(y, N=1, solver="midpoint", noise=eps)
-    model.max_batch = 8
+    model.max_batch = 16
     one = model.enhance(y[1:2], N=1, solver="midpoint", noise=eps[1:2])
     assert torch.equal(full, split)
     assert torch.equal(full[1:2], one)
