@@ -78,14 +78,23 @@ __device__ __forceinline__ float silu_fast(float v) {
   return fmaf(hv, t, hv);
 }
 
+// SiLU(v) from h = v / 2: h + h * tanh(h).  Callers fold the 1/2 into the GroupNorm scale / shift (exact: a
+// power-of-two factor commutes with the fma's rounding), which saves the multiply of silu_fast per element.
+__device__ __forceinline__ float silu_from_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// bf16 -> fp32 is a 16-bit shift: one shift for the low half, one mask for the high half
+// (__bfloat1622float2 compiles to PRMT + IMAD for the high half: three instructions per pair)
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
-  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
-  return __bfloat1622float2(t);
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
 
 // ----------------------------------------------------------------------------

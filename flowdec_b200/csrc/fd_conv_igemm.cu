@@ -73,8 +73,14 @@ struct ConvCfg {
 // GroupNorm partial sums of the 32 columns over the warp's 32 rows.  The column reduction is a
 // transpose-reduce butterfly (31 shuffles per statistic instead of 32*5): after the xor-16 step
 // every lane keeps 16 columns, ... after xor-1 lane L holds the total of column L.
+// Column statistics of the warp's 32 x 32 block.  `scratch` (shared-window address of a 32 x 36-float tile owned by
+// this warp, or 0): transpose through shared memory — 8 conflict-free 16-byte stores + 32 conflict-free loads +
+// 64 adds/FMAs per lane — instead of the register butterfly (62 shuffles + 124 selects + 62 adds).
+#ifndef FD_EPI_STATS_SMEM
+#define FD_EPI_STATS_SMEM 1
+#endif
 __device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], uint32_t bs_addr, uint32_t rowp_addr,
-                                              int row, int j0, float* stat_dst, int lane) {
+                                              int row, int j0, float* stat_dst, int lane, uint32_t scratch = 0) {
   float f[32];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -93,7 +99,24 @@ __device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], uint32_t 
     q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
     sts128(rowp_addr + static_cast<uint32_t>(((j0 + j) ^ (row & 7)) << 4), q);
   }
-  if (stat_dst != nullptr) {
+  if (stat_dst != nullptr && scratch != 0) {
+    __syncwarp();                                    // the previous half's column reads are done
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(scratch + static_cast<uint32_t>(lane * 144 + i * 16)),
+                   "f"(f[4 * i]), "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3]) : "memory");
+    __syncwarp();
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; r += 2) {
+      float a, b;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(scratch + static_cast<uint32_t>(r * 144 + lane * 4)));
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(scratch + static_cast<uint32_t>((r + 1) * 144 + lane * 4)));
+      s0 += a; q0 = fmaf(a, a, q0);
+      s1 += b; q1 = fmaf(b, b, q1);
+    }
+    *reinterpret_cast<float2*>(stat_dst + lane * 2) = make_float2(s0 + s1, q0 + q1);
+  } else if (stat_dst != nullptr) {
     float q[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) q[i] = f[i] * f[i];
@@ -415,8 +438,9 @@ struct HaloCfg {
   static constexpr int kOutBytes = 2 * kTileM * 128;
   static constexpr int kSsFloats = 2 * 512;   // scale/shift of up to 512 transformed channels
   static constexpr int kTmemCols = (2 * N <= 256) ? 256 : 512;
+  static constexpr int kStatScratch = FD_EPI_STATS_SMEM ? 4 * 32 * 36 * 4 : 0;   // per epilogue warp: 32 x 36 floats
   static constexpr int kSmemBytes = 1024 + kStagesA * kHaloStageBytes + kStagesB * kBBytes + kOutBytes + N * 4 +
-                                    kSsFloats * 4 + 512;
+                                    kSsFloats * 4 + 512 + kStatScratch;
 };
 
 // Transform-warp placement.  FD_XF_LAYOUT 0 (default): warps 7..14 (two of them share the MMA warp's scheduler
@@ -610,6 +634,9 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
     const int ew = warp & 3;
     const int row = ew * 32 + lane;       // = hl * 8 + wl of the 16 x 8 tile
     const bool leader = (threadIdx.x == 64);
+    // per-warp 32 x 36-float tile behind the barrier block (column statistics by shared-memory transpose)
+    const uint32_t stat_scratch =
+        FD_EPI_STATS_SMEM ? smem_u32(reinterpret_cast<uint8_t*>(bars) + 512) + static_cast<uint32_t>(ew) * 4608u : 0u;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
@@ -635,14 +662,15 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + ch * 64, v);
           tmem_ld_wait();
-          epilogue_half(v, bs, rowp, row, 0, stat_row ? stat_row + (ch * 64) * 2 : nullptr, lane);
+          epilogue_half(v, bs, rowp, row, 0, stat_row ? stat_row + (ch * 64) * 2 : nullptr, lane, stat_scratch);
           tmem_ld_32x32b_x32(t_row + ch * 64 + 32, v);
           tmem_ld_wait();
           if (ch == kChunks - 1) {
             tc_fence_before_sync();
             mbar_arrive_remote(&tempty_bar[acc], 0);
           }
-          epilogue_half(v, bs + 128, rowp, row, 4, stat_row ? stat_row + (ch * 64 + 32) * 2 : nullptr, lane);
+          epilogue_half(v, bs + 128, rowp, row, 4, stat_row ? stat_row + (ch * 64 + 32) * 2 : nullptr, lane,
+                        stat_scratch);
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
@@ -683,6 +711,16 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
         named_bar_sync(3, 256);
         cur_n = n;
       }
+      // in-image mask of this thread's box rows r = g + 32 i (depends on the tile only, not on the k-slice)
+      constexpr int kItems = (kHaloPix + 31) / 32;       // 6 rows per thread (the last one partial)
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) {
+        const int r = g + 32 * i;
+        const int hh = r / kHaloCols, ww = r - hh * kHaloCols;
+        const int hy = h0 - 1 + hh, wx = w0 - 1 + ww;
+        if ((r < kHaloPix) && hy >= 0 && hy < p.H && wx >= 0 && wx < p.W) okmask |= 1u << i;
+      }
       for (int s = 0; s < p.nseg; ++s) {
         const bool xf = p.seg_ss[s] != nullptr;
         for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
@@ -695,24 +733,22 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float4 q = lds_f4(ss_addr + e * 16);
-              sc[2 * e] = q.x; sh[2 * e] = q.y; sc[2 * e + 1] = q.z; sh[2 * e + 1] = q.w;
+              // halved: the transform evaluates SiLU from v / 2 (silu_from_half)
+              sc[2 * e] = 0.5f * q.x; sh[2 * e] = 0.5f * q.y; sc[2 * e + 1] = 0.5f * q.z; sh[2 * e + 1] = 0.5f * q.w;
             }
             const uint32_t base = smem_u32(sA + sa * kHaloStageBytes) + static_cast<uint32_t>(slot);
-            constexpr int kItems = (kHaloPix + 31) / 32;     // 6 rows per thread (the last one partial)
-            // phase 1: issue every load (independent -> the LSU pipelines them)
+            // phase 1: issue every load (independent -> the LSU pipelines them).  Branch-free: out-of-image rows
+            // hold TMA zero fill and are transformed like the others, then masked to zero (the conv's padding
+            // is zero AFTER the activation); only the partial last item is predicated.
             uint4 raw[kItems];
-            bool ok[kItems];
 #pragma unroll
             for (int i = 0; i < kItems; ++i) {
               const int r = g + 32 * i;
-              const int hh = r / kHaloCols, ww = r - hh * kHaloCols;
-              const int hy = h0 - 1 + hh, wx = w0 - 1 + ww;
-              ok[i] = (r < kHaloPix) && hy >= 0 && hy < p.H && wx >= 0 && wx < p.W;
               raw[i] = make_uint4(0u, 0u, 0u, 0u);
-              if (ok[i]) raw[i] = lds128(base + static_cast<uint32_t>(r) * 128u);
+              if (i < kItems - 1 || r < kHaloPix) raw[i] = lds128(base + static_cast<uint32_t>(r) * 128u);
             }
             if (p.dbg) { const long long now = clock64(); x_ld += now - xq; }
-            // phase 2: affine + SiLU (one MUFU op per element) and store back; out-of-image rows -> 0
+            // phase 2: affine + SiLU (one MUFU op per element) and store back
             if (p.xf_mode == 2) {
               uint32_t acc_x = 0;
 #pragma unroll
@@ -722,16 +758,15 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
 #pragma unroll
             for (int i = 0; i < kItems; ++i) {
               const int r = g + 32 * i;
-              if (r < kHaloPix) {
-                uint4 q = make_uint4(0u, 0u, 0u, 0u);
-                if (ok[i]) {
-                  const float2 a0 = unpack_bf16x2(raw[i].x), a1 = unpack_bf16x2(raw[i].y),
-                               a2 = unpack_bf16x2(raw[i].z), a3 = unpack_bf16x2(raw[i].w);
-                  q.x = pack_bf16x2(silu_fast(fmaf(a0.x, sc[0], sh[0])), silu_fast(fmaf(a0.y, sc[1], sh[1])));
-                  q.y = pack_bf16x2(silu_fast(fmaf(a1.x, sc[2], sh[2])), silu_fast(fmaf(a1.y, sc[3], sh[3])));
-                  q.z = pack_bf16x2(silu_fast(fmaf(a2.x, sc[4], sh[4])), silu_fast(fmaf(a2.y, sc[5], sh[5])));
-                  q.w = pack_bf16x2(silu_fast(fmaf(a3.x, sc[6], sh[6])), silu_fast(fmaf(a3.y, sc[7], sh[7])));
-                }
+              if (i < kItems - 1 || r < kHaloPix) {
+                const uint32_t m = 0u - ((okmask >> i) & 1u);      // all ones inside the image
+                const float2 a0 = unpack_bf16x2(raw[i].x), a1 = unpack_bf16x2(raw[i].y),
+                             a2 = unpack_bf16x2(raw[i].z), a3 = unpack_bf16x2(raw[i].w);
+                uint4 q;
+                q.x = m & pack_bf16x2(silu_from_half(fmaf(a0.x, sc[0], sh[0])), silu_from_half(fmaf(a0.y, sc[1], sh[1])));
+                q.y = m & pack_bf16x2(silu_from_half(fmaf(a1.x, sc[2], sh[2])), silu_from_half(fmaf(a1.y, sc[3], sh[3])));
+                q.z = m & pack_bf16x2(silu_from_half(fmaf(a2.x, sc[4], sh[4])), silu_from_half(fmaf(a2.y, sc[5], sh[5])));
+                q.w = m & pack_bf16x2(silu_from_half(fmaf(a3.x, sc[6], sh[6])), silu_from_half(fmaf(a3.y, sc[7], sh[7])));
                 if (p.xf_mode != 3 || q.x == 0x12345678u) sts128(base + static_cast<uint32_t>(r) * 128u, q);
               }
             }

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kFtThreads, 2) fir_tile_kernel(const __grid_co
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 v = __ldg(ss + i);
-        sc[2 * i] = v.x; sh[2 * i] = v.y; sc[2 * i + 1] = v.z; sh[2 * i + 1] = v.w;
+        sc[2 * i] = 0.5f * v.x; sh[2 * i] = 0.5f * v.y; sc[2 * i + 1] = 0.5f * v.z; sh[2 * i + 1] = 0.5f * v.w;   // silu_from_half
       }
       mbar_wait(&full[s], (it >> 1) & 1);
 #pragma unroll 2
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(kFtThreads, 2) fir_tile_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 f = unpack_bf16x2(w[i]);
-          a[2 * i] = in ? silu_fast(fmaf(f.x, sc[2 * i], sh[2 * i])) : 0.f;
-          a[2 * i + 1] = in ? silu_fast(fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1])) : 0.f;
+          a[2 * i] = in ? silu_from_half(fmaf(f.x, sc[2 * i], sh[2 * i])) : 0.f;
+          a[2 * i + 1] = in ? silu_from_half(fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1])) : 0.f;
         }
         const uint32_t d = act_s + px * 256 + oct * 32;
         sts_f4(d, a[0], a[1], a[2], a[3]);
