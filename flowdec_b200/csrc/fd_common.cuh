@@ -78,12 +78,43 @@ __device__ __forceinline__ float silu_fast(float v) {
   return fmaf(hv, t, hv);
 }
 
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, one issue slot for two IEEE fp32 results, same rounding as
+// the scalar forms).  Used where a warp's ALU work competes with the tensor pipe for power / issue slots.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
 // SiLU(v) from h = v / 2: h + h * tanh(h).  Callers fold the 1/2 into the GroupNorm scale / shift (exact: a
 // power-of-two factor commutes with the fma's rounding), which saves the multiply of silu_fast per element.
 __device__ __forceinline__ float silu_from_half(float h) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
+}
+
+// two SiLUs from a pair of half-arguments: 2 MUFU + 1 FFMA2
+__device__ __forceinline__ float2 silu2_from_half(float2 h) {
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+  return ffma2(h, t, h);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -23,6 +23,8 @@
 //               fp32 accumulators in TMEM, double-buffered (2 x Npad columns).
 //   warps 2..5  epilogue: tcgen05.ld -> +bias -> bf16 -> swizzled smem -> TMA store
 //               (or fp32 direct stores for the 4-channel pyramid convs).
+#include <type_traits>
+
 #include "fd_common.cuh"
 
 #include <algorithm>
@@ -85,10 +87,11 @@ __device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], uint32_t 
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 b4 = lds_f4(bs_addr + i * 16);      // bias (warp-wide broadcast read)
-    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
-    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
-    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+    const float2 lo = fadd2(make_float2(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1])),
+                            make_float2(b4.x, b4.y));
+    const float2 hi = fadd2(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])),
+                            make_float2(b4.z, b4.w));
+    f[4 * i + 0] = lo.x; f[4 * i + 1] = lo.y; f[4 * i + 2] = hi.x; f[4 * i + 3] = hi.y;
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -106,16 +109,16 @@ __device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], uint32_t 
       asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(scratch + static_cast<uint32_t>(lane * 144 + i * 16)),
                    "f"(f[4 * i]), "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3]) : "memory");
     __syncwarp();
-    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);   // (even rows, odd rows)
 #pragma unroll
     for (int r = 0; r < 32; r += 2) {
-      float a, b;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(scratch + static_cast<uint32_t>(r * 144 + lane * 4)));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(scratch + static_cast<uint32_t>((r + 1) * 144 + lane * 4)));
-      s0 += a; q0 = fmaf(a, a, q0);
-      s1 += b; q1 = fmaf(b, b, q1);
+      float2 ab;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ab.x) : "r"(scratch + static_cast<uint32_t>(r * 144 + lane * 4)));
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ab.y) : "r"(scratch + static_cast<uint32_t>((r + 1) * 144 + lane * 4)));
+      s2 = fadd2(s2, ab);
+      q2 = ffma2(ab, ab, q2);
     }
-    *reinterpret_cast<float2*>(stat_dst + lane * 2) = make_float2(s0 + s1, q0 + q1);
+    *reinterpret_cast<float2*>(stat_dst + lane * 2) = make_float2(s2.x + s2.y, q2.x + q2.y);
   } else if (stat_dst != nullptr) {
     float q[32];
 #pragma unroll
@@ -706,13 +709,21 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           if (p.seg_ss[s] == nullptr) continue;
           const float2* src = reinterpret_cast<const float2*>(p.seg_ss[s]) + static_cast<size_t>(n) * p.seg_ss_pitch[s];
           float2* dst = reinterpret_cast<float2*>(sSS) + p.seg_ss_off[s];
-          for (int c = tx; c < p.seg_cin[s]; c += 256) dst[c] = src[c];
+          // halved (SiLU is evaluated from v / 2, silu2_from_half) and laid out per channel pair as
+          // (scale_c, scale_c+1, shift_c, shift_c+1): one 16-byte load yields the two fp32x2 operands
+          float* dstf = reinterpret_cast<float*>(dst);
+          for (int c = tx; c < p.seg_cin[s]; c += 256) {
+            const float2 v = src[c];
+            dstf[(c >> 1) * 4 + (c & 1)] = 0.5f * v.x;
+            dstf[(c >> 1) * 4 + 2 + (c & 1)] = 0.5f * v.y;
+          }
         }
         named_bar_sync(3, 256);
         cur_n = n;
       }
       // in-image mask of this thread's box rows r = g + 32 i (depends on the tile only, not on the k-slice)
       constexpr int kItems = (kHaloPix + 31) / 32;       // 6 rows per thread (the last one partial)
+      const bool interior = h0 > 0 && h0 + kHaloTileH < p.H && w0 > 0 && w0 + kHaloTileW < p.W;
       uint32_t okmask = 0;
 #pragma unroll
       for (int i = 0; i < kItems; ++i) {
@@ -728,13 +739,13 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           mbar_wait(&fullA[sa], pa);
           if (p.dbg) { const long long now = clock64(); x_wait += now - xq; xq = now; }
           if (xf && p.xf_mode != 1) {
-            float sc[8], sh[8];
+            float2 sc2[4], sh2[4];                  // (scale, shift) / 2 of channel pairs 2e, 2e+1
             const uint32_t ss_addr = smem_u32(sSS) + static_cast<uint32_t>(p.seg_ss_off[s] + ks * kSliceK + j * 8) * 8u;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float4 q = lds_f4(ss_addr + e * 16);
-              // halved: the transform evaluates SiLU from v / 2 (silu_from_half)
-              sc[2 * e] = 0.5f * q.x; sh[2 * e] = 0.5f * q.y; sc[2 * e + 1] = 0.5f * q.z; sh[2 * e + 1] = 0.5f * q.w;
+              sc2[e] = make_float2(q.x, q.y);
+              sh2[e] = make_float2(q.z, q.w);
             }
             const uint32_t base = smem_u32(sA + sa * kHaloStageBytes) + static_cast<uint32_t>(slot);
             // phase 1: issue every load (independent -> the LSU pipelines them).  Branch-free: out-of-image rows
@@ -754,21 +765,27 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
 #pragma unroll
               for (int i = 0; i < kItems; ++i) acc_x ^= raw[i].x ^ raw[i].y ^ raw[i].z ^ raw[i].w;
               if (acc_x == 0x12345678u) sts128(base, raw[0]);      // keep the loads alive
-            } else
+            } else {
+              auto transform_rows = [&](auto masked) {
 #pragma unroll
-            for (int i = 0; i < kItems; ++i) {
-              const int r = g + 32 * i;
-              if (i < kItems - 1 || r < kHaloPix) {
-                const uint32_t m = 0u - ((okmask >> i) & 1u);      // all ones inside the image
-                const float2 a0 = unpack_bf16x2(raw[i].x), a1 = unpack_bf16x2(raw[i].y),
-                             a2 = unpack_bf16x2(raw[i].z), a3 = unpack_bf16x2(raw[i].w);
-                uint4 q;
-                q.x = m & pack_bf16x2(silu_from_half(fmaf(a0.x, sc[0], sh[0])), silu_from_half(fmaf(a0.y, sc[1], sh[1])));
-                q.y = m & pack_bf16x2(silu_from_half(fmaf(a1.x, sc[2], sh[2])), silu_from_half(fmaf(a1.y, sc[3], sh[3])));
-                q.z = m & pack_bf16x2(silu_from_half(fmaf(a2.x, sc[4], sh[4])), silu_from_half(fmaf(a2.y, sc[5], sh[5])));
-                q.w = m & pack_bf16x2(silu_from_half(fmaf(a3.x, sc[6], sh[6])), silu_from_half(fmaf(a3.y, sc[7], sh[7])));
-                if (p.xf_mode != 3 || q.x == 0x12345678u) sts128(base + static_cast<uint32_t>(r) * 128u, q);
-              }
+                for (int i = 0; i < kItems; ++i) {
+                  const int r = g + 32 * i;
+                  if (i < kItems - 1 || r < kHaloPix) {
+                    const uint32_t m = decltype(masked)::value ? 0u - ((okmask >> i) & 1u) : 0xffffffffu;
+                    const uint32_t w4[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+                    uint32_t o4[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {          // two channels per packed fp32x2 operation
+                      const float2 y = silu2_from_half(ffma2(unpack_bf16x2(w4[e]), sc2[e], sh2[e]));
+                      o4[e] = m & pack_bf16x2(y.x, y.y);
+                    }
+                    uint4 q = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                    if (p.xf_mode != 3 || q.x == 0x12345678u) sts128(base + static_cast<uint32_t>(r) * 128u, q);
+                  }
+                }
+              };
+              // ~90 % of the tiles do not touch the image border: no masking needed there (block-uniform branch)
+              if (interior) transform_rows(std::false_type{}); else transform_rows(std::true_type{});
             }
             long long f0 = 0;
             if (p.dbg) f0 = clock64();
