@@ -50,10 +50,10 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__device__ __forceinline__ void stg64_bf16(__nv_bfloat16* p, const float (&v)[4]) {
+__device__ __forceinline__ void stg64_bf16(__nv_bfloat16* p, const float2 (&v)[2]) {
   uint2 r;
-  r.x = pack_bf16x2(v[0], v[1]);
-  r.y = pack_bf16x2(v[2], v[3]);
+  r.x = pack_bf16x2(v[0].x, v[0].y);
+  r.y = pack_bf16x2(v[1].x, v[1].y);
   *reinterpret_cast<uint2*>(p) = r;
 }
 
@@ -115,13 +115,14 @@ __global__ void __launch_bounds__(kFtThreads, 2) fir_tile_kernel(const __grid_co
     // ---- phase A: box -> SiLU(scale * x + shift) in fp32 (zero outside the image), once per pixel
     {
       const int oct = tid & 7;
-      float sc[8], sh[8];
+      float2 sc2[4], sh2[4];            // (scale, shift) / 2 of channel pairs: SiLU is evaluated from v / 2
       const float4* ss = reinterpret_cast<const float4*>(
           p.scale_shift + (static_cast<size_t>(q.b) * C + q.g * 64 + oct * 8) * 2);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 v = __ldg(ss + i);
-        sc[2 * i] = 0.5f * v.x; sh[2 * i] = 0.5f * v.y; sc[2 * i + 1] = 0.5f * v.z; sh[2 * i + 1] = 0.5f * v.w;   // silu_from_half
+        sc2[i] = make_float2(0.5f * v.x, 0.5f * v.z);
+        sh2[i] = make_float2(0.5f * v.y, 0.5f * v.w);
       }
       mbar_wait(&full[s], (it >> 1) & 1);
 #pragma unroll 2
@@ -131,16 +132,15 @@ __global__ void __launch_bounds__(kFtThreads, 2) fir_tile_kernel(const __grid_co
                         static_cast<unsigned>(q.c0 - 1 + pc) < static_cast<unsigned>(p.W);
         const uint4 r = lds128(raw_s + px * 128 + oct * 16);
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-        float a[8];
+        float2 a[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = unpack_bf16x2(w[i]);
-          a[2 * i] = in ? silu_from_half(fmaf(f.x, sc[2 * i], sh[2 * i])) : 0.f;
-          a[2 * i + 1] = in ? silu_from_half(fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1])) : 0.f;
+        for (int i = 0; i < 4; ++i) {      // packed fp32x2: two channels per FFMA2
+          const float2 y = silu2_from_half(ffma2(unpack_bf16x2(w[i]), sc2[i], sh2[i]));
+          a[i] = in ? y : make_float2(0.f, 0.f);
         }
         const uint32_t d = act_s + px * 256 + oct * 32;
-        sts_f4(d, a[0], a[1], a[2], a[3]);
-        sts_f4(d + 16, a[4], a[5], a[6], a[7]);
+        sts_f4(d, a[0].x, a[0].y, a[1].x, a[1].y);
+        sts_f4(d + 16, a[2].x, a[2].y, a[3].x, a[3].y);
       }
     }
     __syncthreads();
@@ -153,44 +153,47 @@ __global__ void __launch_bounds__(kFtThreads, 2) fir_tile_kernel(const __grid_co
       __nv_bfloat16* o_act = p.out + ((static_cast<size_t>(q.b) * Ho + 2 * q.r0) * Wo + 2 * (q.c0 + col)) * C + ch;
       __nv_bfloat16* o_raw = p.out_raw + (o_act - p.out);
       const size_t row_pitch = static_cast<size_t>(Wo) * C;
-      float pE[4], pF[4], prE[4], prF[4];                     // horizontal pair of the previous box row
+      // all FIR arithmetic on channel pairs (fp32x2): v[0] = channels 0,1, v[1] = channels 2,3 of the slice
+      const float2 k25 = make_float2(0.25f, 0.25f), k75 = make_float2(0.75f, 0.75f);
+      float2 pE[2], pF[2], prE[2], prF[2];                    // horizontal pair of the previous box row
 #pragma unroll
       for (int br = 0; br < kFtBoxH; ++br) {
         const int px = br * kFtBoxW + col;
-        float cE[4], cF[4], crE[4], crF[4];
+        float2 cE[2], cF[2], crE[2], crF[2];
         {
           const float4 l = lds_f4(act_s + px * 256 + slice * 16);
           const float4 m = lds_f4(act_s + (px + 1) * 256 + slice * 16);
           const float4 r = lds_f4(act_s + (px + 2) * 256 + slice * 16);
-          const float lv[4] = {l.x, l.y, l.z, l.w}, mv[4] = {m.x, m.y, m.z, m.w}, rv[4] = {r.x, r.y, r.z, r.w};
+          const float2 lv[2] = {make_float2(l.x, l.y), make_float2(l.z, l.w)};
+          const float2 mv[2] = {make_float2(m.x, m.y), make_float2(m.z, m.w)};
+          const float2 rv[2] = {make_float2(r.x, r.y), make_float2(r.z, r.w)};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            cE[c] = fmaf(0.75f, mv[c], 0.25f * lv[c]);
-            cF[c] = fmaf(0.75f, mv[c], 0.25f * rv[c]);
+          for (int c = 0; c < 2; ++c) {
+            cE[c] = ffma2(k75, mv[c], fmul2(k25, lv[c]));
+            cF[c] = ffma2(k75, mv[c], fmul2(k25, rv[c]));
           }
         }
         {
           const uint2 l = lds64(raw_s + px * 128 + slice * 8);
           const uint2 m = lds64(raw_s + (px + 1) * 128 + slice * 8);
           const uint2 r = lds64(raw_s + (px + 2) * 128 + slice * 8);
-          const float2 l0 = unpack_bf16x2(l.x), l1 = unpack_bf16x2(l.y), m0 = unpack_bf16x2(m.x),
-                       m1 = unpack_bf16x2(m.y), r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y);
-          const float lv[4] = {l0.x, l0.y, l1.x, l1.y}, mv[4] = {m0.x, m0.y, m1.x, m1.y},
-                      rv[4] = {r0.x, r0.y, r1.x, r1.y};
+          const float2 lv[2] = {unpack_bf16x2(l.x), unpack_bf16x2(l.y)};
+          const float2 mv[2] = {unpack_bf16x2(m.x), unpack_bf16x2(m.y)};
+          const float2 rv[2] = {unpack_bf16x2(r.x), unpack_bf16x2(r.y)};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            crE[c] = fmaf(0.75f, mv[c], 0.25f * lv[c]);
-            crF[c] = fmaf(0.75f, mv[c], 0.25f * rv[c]);
+          for (int c = 0; c < 2; ++c) {
+            crE[c] = ffma2(k75, mv[c], fmul2(k25, lv[c]));
+            crF[c] = ffma2(k75, mv[c], fmul2(k25, rv[c]));
           }
         }
         if (br >= 1 && br <= 8) {       // current row is tile row i = br - 1: out row 2i = .25 prev + .75 cur
-          float e[4], f[4], re[4], rf[4];
+          float2 e[2], f[2], re[2], rf[2];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            e[c] = fmaf(0.75f, cE[c], 0.25f * pE[c]);
-            f[c] = fmaf(0.75f, cF[c], 0.25f * pF[c]);
-            re[c] = fmaf(0.75f, crE[c], 0.25f * prE[c]);
-            rf[c] = fmaf(0.75f, crF[c], 0.25f * prF[c]);
+          for (int c = 0; c < 2; ++c) {
+            e[c] = ffma2(k75, cE[c], fmul2(k25, pE[c]));
+            f[c] = ffma2(k75, cF[c], fmul2(k25, pF[c]));
+            re[c] = ffma2(k75, crE[c], fmul2(k25, prE[c]));
+            rf[c] = ffma2(k75, crF[c], fmul2(k25, prF[c]));
           }
           const size_t off = static_cast<size_t>(2 * (br - 1)) * row_pitch;
           stg64_bf16(o_act + off, e);
@@ -199,13 +202,13 @@ __global__ void __launch_bounds__(kFtThreads, 2) fir_tile_kernel(const __grid_co
           stg64_bf16(o_raw + off + C, rf);
         }
         if (br >= 2) {                  // previous row is tile row i = br - 2: out row 2i+1 = .75 prev + .25 cur
-          float e[4], f[4], re[4], rf[4];
+          float2 e[2], f[2], re[2], rf[2];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            e[c] = fmaf(0.75f, pE[c], 0.25f * cE[c]);
-            f[c] = fmaf(0.75f, pF[c], 0.25f * cF[c]);
-            re[c] = fmaf(0.75f, prE[c], 0.25f * crE[c]);
-            rf[c] = fmaf(0.75f, prF[c], 0.25f * crF[c]);
+          for (int c = 0; c < 2; ++c) {
+            e[c] = ffma2(k75, pE[c], fmul2(k25, cE[c]));
+            f[c] = ffma2(k75, pF[c], fmul2(k25, cF[c]));
+            re[c] = ffma2(k75, prE[c], fmul2(k25, crE[c]));
+            rf[c] = ffma2(k75, prF[c], fmul2(k25, crF[c]));
           }
           const size_t off = static_cast<size_t>(2 * (br - 2) + 1) * row_pitch;
           stg64_bf16(o_act + off, e);
@@ -214,36 +217,37 @@ __global__ void __launch_bounds__(kFtThreads, 2) fir_tile_kernel(const __grid_co
           stg64_bf16(o_raw + off + C, rf);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           pE[c] = cE[c]; pF[c] = cF[c]; prE[c] = crE[c]; prF[c] = crF[c];
         }
       }
     } else {
       const int Ho = p.H / 2, Wo = p.W / 2;
-      const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+      const float2 k2[4] = {make_float2(0.125f, 0.125f), make_float2(0.375f, 0.375f), make_float2(0.375f, 0.375f),
+                            make_float2(0.125f, 0.125f)};
+      const float2 z2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int opx = (tid >> 4) + 16 * u;                  // 4 x 8 output pixels
         const int orow = opx >> 3, ocol = opx & 7;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f}, racc[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 acc[2] = {z2, z2}, racc[2] = {z2, z2};         // channel pairs (0,1), (2,3): fp32x2 arithmetic
 #pragma unroll
         for (int ri = 0; ri < 4; ++ri) {
           const int px = (2 * orow + ri) * kFtBoxW + 2 * ocol;
-          float h[4] = {0.f, 0.f, 0.f, 0.f}, rh[4] = {0.f, 0.f, 0.f, 0.f};
+          float2 h[2] = {z2, z2}, rh[2] = {z2, z2};
 #pragma unroll
           for (int ci = 0; ci < 4; ++ci) {
             const float4 a = lds_f4(act_s + (px + ci) * 256 + slice * 16);
             const uint2 r = lds64(raw_s + (px + ci) * 128 + slice * 8);
-            const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y);
-            h[0] = fmaf(k[ci], a.x, h[0]); h[1] = fmaf(k[ci], a.y, h[1]);
-            h[2] = fmaf(k[ci], a.z, h[2]); h[3] = fmaf(k[ci], a.w, h[3]);
-            rh[0] = fmaf(k[ci], r0.x, rh[0]); rh[1] = fmaf(k[ci], r0.y, rh[1]);
-            rh[2] = fmaf(k[ci], r1.x, rh[2]); rh[3] = fmaf(k[ci], r1.y, rh[3]);
+            h[0] = ffma2(k2[ci], make_float2(a.x, a.y), h[0]);
+            h[1] = ffma2(k2[ci], make_float2(a.z, a.w), h[1]);
+            rh[0] = ffma2(k2[ci], unpack_bf16x2(r.x), rh[0]);
+            rh[1] = ffma2(k2[ci], unpack_bf16x2(r.y), rh[1]);
           }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            acc[c] = fmaf(k[ri], h[c], acc[c]);
-            racc[c] = fmaf(k[ri], rh[c], racc[c]);
+          for (int c = 0; c < 2; ++c) {
+            acc[c] = ffma2(k2[ri], h[c], acc[c]);
+            racc[c] = ffma2(k2[ri], rh[c], racc[c]);
           }
         }
         const size_t off =
