@@ -258,8 +258,6 @@ class FlowModel(EnhancementModel):
             raise NotImplementedError("return_traj is not available for ragged batches")
         solver = get_solver(solver)
         dev = self.device
-        if dev.type != "cuda":
-            raise RuntimeError("flowdec_b200 runs on CUDA (sm_100a) only; call model.cuda()")
         if y.ndim == 2:
             y = y.unsqueeze(1)
         if y.ndim != 3 or y.shape[1] != 1:
@@ -274,6 +272,8 @@ class FlowModel(EnhancementModel):
         if len(buckets) != 1:
             raise ValueError(f"clips of one ragged batch must share the padded-frame bucket, got {sorted(buckets)}; "
                              "use flowdec_b200.batching.enhance_list to bucket a list of clips")
+        if dev.type != "cuda":
+            raise RuntimeError("flowdec_b200 runs on CUDA (sm_100a) only; call model.cuda()")
         Tp = buckets.pop()
         pitch = Tp * 384
         key = ("ragged", B, Tp, int(N), solver, float(sigma_fac))

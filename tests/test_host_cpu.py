@@ -109,3 +109,25 @@ def test_length_bucketed_batching_host_logic():
         bucket_by_frames([96000], 0)
     y, l = pad_batch([torch.arange(5.0), torch.ones(1, 3)])
     assert y.shape == (2, 1, 5) and l == [5, 3] and y[1, 0].tolist() == [1, 1, 1, 0, 0]
+
+
+def test_ragged_enhance_argument_checks():
+    """FlowModel.enhance(lengths=): shape / length / bucket validation happens before any device work;
+    without a CUDA device the call then fails loudly instead of falling back"""
+    import torch
+    m = build_flowdec("75m")
+    y = torch.zeros(2, 1, 96000)
+    with pytest.raises(ValueError, match="lengths for a batch"):
+        m.enhance(y, N=1, lengths=[96000])
+    with pytest.raises(ValueError, match="clip lengths must be in"):
+        m.enhance(y, N=1, lengths=[96000, 700])
+    with pytest.raises(ValueError, match="clip lengths must be in"):
+        m.enhance(y, N=1, lengths=[96000, 96001])
+    with pytest.raises(ValueError, match="padded-frame bucket"):
+        m.enhance(y, N=1, lengths=[96000, 48000])
+    with pytest.raises(ValueError, match="ragged batches are"):
+        m.enhance(torch.zeros(2, 2, 96000), N=1, lengths=[96000, 96000])
+    with pytest.raises(NotImplementedError):
+        m.enhance(y, N=1, lengths=[96000, 96000], return_traj=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.enhance(y, N=1, lengths=[96000, 95000])
