@@ -8,7 +8,6 @@ state_dict keys.  No lightning / hydra / torchdyn / torchcfm dependency: the ODE
 fused kernel launches (flowdec_b200/sampling/solvers.py), optionally captured as one CUDA graph
 per (batch, length, N, solver).
 """
-import warnings
 from typing import Optional
 
 import numpy as np
@@ -16,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .sampling.solvers import get_solver, nfe_per_step, stages, t_grid
+from .sampling.solvers import get_solver, stages, t_grid
 from .util.other import padded_frames
 
 

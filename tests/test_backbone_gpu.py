@@ -13,7 +13,6 @@ import torch
 
 from flowdec_b200.model import build_flowdec
 from flowdec_b200.util.synth import synth_state_dict
-from oracle import flowdec_oracle as O
 from oracle.make_golden import golden_inputs
 
 pytestmark = pytest.mark.gpu

@@ -1,5 +1,4 @@
 """GPU: the file-level CLI (enhance.py) on a synthetic checkpoint and wav files."""
-import os
 
 import numpy as np
 import pytest

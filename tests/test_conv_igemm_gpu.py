@@ -2,13 +2,11 @@
 the same bf16-rounded operands.  Tolerance: fp32-accumulation-order noise + one bf16
 output rounding (rel 2^-8), i.e. |err| <= 1e-2 * max|ref| elementwise is generous while any
 descriptor/layout bug produces O(1) errors."""
-import ctypes
 
 import pytest
 import torch
 import torch.nn.functional as F
 
-from flowdec_b200 import _lib
 from flowdec_b200.ops import conv_igemm, pack_conv_weight
 
 pytestmark = pytest.mark.gpu

@@ -1,5 +1,4 @@
 """CPU tests of the host-side mirror: state_dict contract, solver schedules, C-ABI symbols."""
-import ctypes
 import os
 import re
 

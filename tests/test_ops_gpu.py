@@ -1,7 +1,6 @@
 """GPU parity of the side kernels (fd_elementwise.cu, fd_stft.cu) against the CPU oracle
 (oracle/flowdec_oracle.py) on seeded inputs.  fp32-exact ops: rel-L2 <= 1e-5; bf16-output ops:
 max error <= 2^-8 relative to the tensor scale (one bf16 rounding)."""
-import math
 
 import pytest
 import torch
