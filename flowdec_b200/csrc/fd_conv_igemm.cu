@@ -433,6 +433,14 @@ struct HaloParams {
   int xf_mode;                   // experiments (env FD_HALO_XF_MODE): 0 normal, 1 barriers only, 2 loads only, 3 no stores
 };
 
+// Cycle counters and ablation modes of the halo kernel (tools/halo_dbg.py) are compiled in only with
+// -DFD_HALO_DEBUG=1 (python tools/ab_bench.py --build "-DFD_HALO_DEBUG=1"); the product build carries none of it.
+#ifndef FD_HALO_DEBUG
+#define FD_HALO_DEBUG 0
+#endif
+#define FD_DBG (FD_HALO_DEBUG && p.dbg != nullptr)
+#define FD_XF_MODE (FD_HALO_DEBUG ? p.xf_mode : 0)
+
 template <int N>
 struct HaloCfg {
   static constexpr int kStagesA = 3;
@@ -570,12 +578,12 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
       int acc = 0, issued = 0;
       uint32_t acc_phase = 0;
       long long w_tempty = 0, w_ready = 0, w_fullb = 0, tq = 0;
-      const long long t_begin = p.dbg ? clock64() : 0;
+      const long long t_begin = FD_DBG ? clock64() : 0;
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
         ++issued;
-        if (p.dbg) tq = clock64();
+        if (FD_DBG) tq = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
-        if (p.dbg) w_tempty += clock64() - tq;
+        if (FD_DBG) w_tempty += clock64() - tq;
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * N);
         uint32_t first = 1;
@@ -583,18 +591,18 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           const int ntap = p.seg_taps[s];
           const bool last_seg = (s == p.nseg - 1);
           for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
-            if (p.dbg) tq = clock64();
+            if (FD_DBG) tq = clock64();
             if (XF) mbar_wait_acquire_cluster(&readyA[sa], pa); else mbar_wait(&readyA[sa], pa);
-            if (p.dbg) w_ready += clock64() - tq;
+            if (FD_DBG) w_ready += clock64() - tq;
             tc_fence_after_sync();
             const uint32_t a_base = smem_u32(sA + sa * kHaloStageBytes);
             const bool last_stage = last_seg && (ks == p.seg_kslices[s] - 1);
             for (int tap = 0; tap < ntap; ++tap) {
               const int dh = (ntap == 9) ? tap / 3 - 1 : 0;
               const int dw = (ntap == 9) ? tap % 3 - 1 : 0;
-              if (p.dbg) tq = clock64();
+              if (FD_DBG) tq = clock64();
               mbar_wait(&fullB[sb], pb);
-              if (p.dbg) w_fullb += clock64() - tq;
+              if (FD_DBG) w_fullb += clock64() - tq;
               tc_fence_after_sync();
               // rows of the box are halo pixels at a 10-pixel pitch: tap view = row offset, SBO = one box row
               const uint64_t da = umma_desc_k_sw128_sbo(
@@ -624,7 +632,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
       if (issued > 0)
         for (int j = (issued >= 2 ? issued - 2 : issued - 1); j < issued; ++j)
           mbar_wait(&tempty_bar[j & 1], static_cast<uint32_t>((j >> 1) & 1));
-      if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+      if (FD_DBG && blockIdx.x == 0 && lane == 0) {
         p.dbg[0] = clock64() - t_begin;
         p.dbg[1] = w_tempty;
         p.dbg[2] = w_ready;
@@ -735,10 +743,10 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
       for (int s = 0; s < p.nseg; ++s) {
         const bool xf = p.seg_ss[s] != nullptr;
         for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
-          if (p.dbg) xq = clock64();
+          if (FD_DBG) xq = clock64();
           mbar_wait(&fullA[sa], pa);
-          if (p.dbg) { const long long now = clock64(); x_wait += now - xq; xq = now; }
-          if (xf && p.xf_mode != 1) {
+          if (FD_DBG) { const long long now = clock64(); x_wait += now - xq; xq = now; }
+          if (xf && FD_XF_MODE != 1) {
             float2 sc2[4], sh2[4];                  // (scale, shift) / 2 of channel pairs 2e, 2e+1
             const uint32_t ss_addr = smem_u32(sSS) + static_cast<uint32_t>(p.seg_ss_off[s] + ks * kSliceK + j * 8) * 8u;
 #pragma unroll
@@ -758,9 +766,9 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
               raw[i] = make_uint4(0u, 0u, 0u, 0u);
               if (i < kItems - 1 || r < kHaloPix) raw[i] = lds128(base + static_cast<uint32_t>(r) * 128u);
             }
-            if (p.dbg) { const long long now = clock64(); x_ld += now - xq; }
+            if (FD_DBG) { const long long now = clock64(); x_ld += now - xq; }
             // phase 2: affine + SiLU (one MUFU op per element) and store back
-            if (p.xf_mode == 2) {
+            if (FD_XF_MODE == 2) {
               uint32_t acc_x = 0;
 #pragma unroll
               for (int i = 0; i < kItems; ++i) acc_x ^= raw[i].x ^ raw[i].y ^ raw[i].z ^ raw[i].w;
@@ -780,7 +788,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
                       o4[e] = m & pack_bf16x2(y.x, y.y);
                     }
                     uint4 q = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-                    if (p.xf_mode != 3 || q.x == 0x12345678u) sts128(base + static_cast<uint32_t>(r) * 128u, q);
+                    if (FD_XF_MODE != 3 || q.x == 0x12345678u) sts128(base + static_cast<uint32_t>(r) * 128u, q);
                   }
                 }
               };
@@ -788,18 +796,18 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
               if (interior) transform_rows(std::false_type{}); else transform_rows(std::true_type{});
             }
             long long f0 = 0;
-            if (p.dbg) f0 = clock64();
+            if (FD_DBG) f0 = clock64();
             fence_proxy_async_smem();
-            if (p.dbg) x_fence += clock64() - f0;
+            if (FD_DBG) x_fence += clock64() - f0;
           }
           __syncwarp();
           if (lane == 0) mbar_arrive_remote_release_cluster(&readyA[sa], 0);
-          if (p.dbg) x_work += clock64() - xq;
+          if (FD_DBG) x_work += clock64() - xq;
           if (++sa == SA) { sa = 0; pa ^= 1u; }
         }
       }
     }
-    if (p.dbg != nullptr && blockIdx.x == 0 && tx == 0) {
+    if (FD_DBG && blockIdx.x == 0 && tx == 0) {
       p.dbg[14] = x_wait;
       p.dbg[15] = x_work;
       p.dbg[12] = x_ld;

@@ -7,7 +7,8 @@ variants are only comparable inside one gpurun call).
                     -> alternates default / variant `bench.py --steps 3 --warmup 3 --no-cpu-baseline` runs
 
 Build-time switches that exist: FD_XF_LAYOUT (transform-warp placement), FD_EPI_STATS_SMEM (column statistics by
-shared-memory transpose vs shuffle butterfly), FD_MBAR_HINT_NS (mbarrier suspend-time hint, 0 = polling loop).
+shared-memory transpose vs shuffle butterfly), FD_MBAR_HINT_NS (mbarrier suspend-time hint, 0 = polling loop),
+FD_HALO_DEBUG (cycle counters + transform ablation modes for tools/halo_dbg.py).
 """
 import json
 import os

@@ -1,6 +1,12 @@
-"""Where does the halo kernel's MMA thread wait?  (cycle counters of block 0)"""
+"""Where does the halo kernel's MMA thread wait?  (cycle counters of block 0, ablation modes of the transform)
+
+The counters exist only in a debug build:  python tools/ab_bench.py --build "-DFD_HALO_DEBUG=1"   (CPU box)
+then on the GPU box:                       python tools/halo_dbg.py    (picks up flowdec_b200/lib_variant.so)"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+if not os.environ.get("FD_LIB_PATH") and os.path.exists(os.path.join(ROOT, "flowdec_b200", "lib_variant.so")):
+    os.environ["FD_LIB_PATH"] = os.path.join(ROOT, "flowdec_b200", "lib_variant.so")
 import torch
 dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
 os.environ["FD_HALO_DBG"] = str(dbg.data_ptr())
