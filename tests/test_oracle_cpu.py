@@ -84,3 +84,26 @@ def test_oracle_vs_live_reference_small():
         ref = net(x, y, t)
         mine = O.ncsnpp_forward(sd, x, y, t, num_resolutions=2)
     assert rel_l2(torch.view_as_real(mine), torch.view_as_real(ref)) < 1e-5
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present on this machine")
+def test_oracle_attention_backbone_vs_live_reference():
+    """SURVEY.md §8f-3 (next row): the SGMSE-style baseline backbone — config/model/backbone/
+    ncsnpp_default_ycond.yaml: 7 levels, 2 res-blocks per level, bottleneck attention, 3x3 output layer — at a
+    reduced width, reference vs oracle"""
+    R = ref_shim.load_reference()
+    kw = dict(ref_shim.BACKBONE_KW)
+    kw.update(image_size=128, nf=16, ch_mult=[1, 1, 2, 2, 2, 2, 2], num_res_blocks=2, bottleneck_attn=True,
+              output_layer_kwargs=dict(kernel_size=3, bias=False, padding="same", padding_mode="zeros"))
+    net = R.ncsnpp.NCSNpp(**kw)
+    sd = synth_state_dict({"backbone." + k: v for k, v in net.state_dict().items()}, seed=4)
+    net.load_state_dict({k[len("backbone."):]: v for k, v in sd.items()})
+    assert any(".NIN_0.W" in k for k in sd)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 1, 128, 192, dtype=torch.complex64, generator=g)   # bottleneck: 2 x 3 tokens
+    y = torch.randn(2, 1, 128, 192, dtype=torch.complex64, generator=g)
+    t = torch.tensor([0.3])
+    with torch.no_grad():
+        ref = net(x, y, t)
+        mine = O.ncsnpp_forward(sd, x, y, t, num_resolutions=7, num_res_blocks=2, bottleneck_attn=True)
+    assert rel_l2(torch.view_as_real(mine), torch.view_as_real(ref)) < 1e-5
