@@ -27,8 +27,10 @@ def synth_tensor(seed, key, like):
     g = _gen(seed, key)
     if key in _KEEP or key.endswith("sigma_y") or key.endswith("sigma_x") or key.endswith(".window"):
         return like.clone()
-    if key.endswith(".W"):  # GaussianFourierProjection, frozen, scale 16 (layerspp.py:47)
+    if key.endswith(".W") and len(shape) == 1:  # GaussianFourierProjection, frozen, scale 16 (layerspp.py:47)
         return torch.randn(shape, generator=g) * 16.0
+    if key.endswith(".b"):  # NIN bias of the attention block (layers.py NIN)
+        return 0.05 * torch.randn(shape, generator=g)
     if len(shape) >= 2:  # conv / linear weight: U(+-sqrt(3/fan_in)) -> unit gain
         fan_in = 1
         for s in shape[1:]:

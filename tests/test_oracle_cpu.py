@@ -107,3 +107,17 @@ def test_oracle_attention_backbone_vs_live_reference():
         ref = net(x, y, t)
         mine = O.ncsnpp_forward(sd, x, y, t, num_resolutions=7, num_res_blocks=2, bottleneck_attn=True)
     assert rel_l2(torch.view_as_real(mine), torch.view_as_real(ref)) < 1e-5
+
+
+def test_oracle_attention_backbone_vs_golden():
+    """same pin without the reference tree: tests/golden/ncsnpp_attn_seed4.npz was produced by the reference itself
+    (oracle/make_golden.py:attn_backbone_golden); the state_dict is rebuilt from the stored key names / shapes"""
+    from oracle.make_golden import attn_golden_inputs
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ncsnpp_attn_seed4.npz"))
+    tmpl = {str(k): torch.empty([int(d) for d in str(s).split(",") if d], dtype=torch.float32)
+            for k, s in zip(G["keys"], G["shapes"])}
+    sd = synth_state_dict(tmpl, seed=4)
+    I = attn_golden_inputs()
+    with torch.no_grad():
+        v = O.ncsnpp_forward(sd, I["X"], I["Y"], I["t"], num_resolutions=7, num_res_blocks=2, bottleneck_attn=True)
+    assert rel_l2(torch.view_as_real(v), torch.from_numpy(G["backbone_v"])) < 1e-5
