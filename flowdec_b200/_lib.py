@@ -67,6 +67,12 @@ SIGNATURES = {
     "fd_dac_conv1d_strided": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "fd_rvq_encode": [_P] * 13 + [_I] * 6 + [_P],
     "fd_fir_tiles_enable": [_I],
+    "fd_upfirdn2d_f32": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "fd_conv2d_direct": [ctypes.POINTER(ConvSrc), _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "fd_attention": [_P, _I, _I, _I, _F, _P, _P],
+    "fd_gn_act_down_any": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P],
+    "fd_conv_in_any": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "fd_output_conv3_axpy": [_P, _P, _P, _F, _P, _F, _P, _F, _F, _P, _P, _I, _I, _I, _P],
 }
 
 
@@ -104,4 +110,7 @@ def stream_ptr():
 def ptr(t):
     if t is None:
         return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        # a host address must never reach a kernel (it faults, or on HMM boxes silently streams over PCIe)
+        raise FlowDecNativeError(f"expected a CUDA tensor, got a {t.device} tensor of shape {tuple(t.shape)}")
     return ctypes.c_void_p(t.data_ptr())

@@ -9,13 +9,19 @@ Drop-in for the reference class `flowdec.backbones.ncsnpp.NCSNpp`
 The nn.Modules below only *hold parameters*.  `forward` never calls their `forward`: it walks
 the network issuing the hand-written sm_100a kernels of libflowdec_b200.so through
 `flowdec_b200.ops` (tcgen05 implicit-GEMM convolutions + HBM-bound GroupNorm/SiLU/FIR
-passes).  Supported configuration family = the one FlowDec ships
-(config/model/backbone/ncsnpp_final_no_attn.yaml): biggan res-blocks, FIR resampling,
-progressive output_skip / input_skip with 'sum' combine, Fourier embedding, no attention.
-Anything else raises NotImplementedError rather than silently running a different path.
+passes).  Supported configuration family = what the reference's configs instantiate:
+biggan res-blocks, FIR resampling, progressive output_skip / input_skip with 'sum' combine,
+Fourier embedding, any nf / ch_mult / num_res_blocks, optional bottleneck attention and a 1x1 or 3x3
+bias-free output layer — i.e. config/model/backbone/ncsnpp_final_no_attn.yaml (FlowDec / ScoreDec) and
+ncsnpp_default_ycond.yaml (the SGMSE-style 7-level baseline).  Convolutions whose shape
+fits the tcgen05 tiles (channel segments % 64, Cout 128/256, W % 8, H % tile height) run on tensor cores;
+the rest (the 24x8 ... 12x1 levels of the 7-level net, narrow test networks) run on the shape-generic
+CUDA-core kernels of csrc/fd_generic.cu.  Anything else raises NotImplementedError rather than silently
+running a different path.
 """
 import ctypes
 import math
+from collections import OrderedDict
 
 import numpy as np
 import torch
@@ -86,6 +92,28 @@ class Combine(nn.Module):
         self.Conv_0 = _conv(dim1, dim2, 1)
 
 
+class NIN(nn.Module):
+    """parameter holder for reference layers.py:566-575 (y = x . W + b over channels)"""
+
+    def __init__(self, in_dim, num_units, init_scale=0.1):
+        super().__init__()
+        self.W = nn.Parameter(_ddpm_uniform_(torch.empty(in_dim, num_units), init_scale))
+        self.b = nn.Parameter(torch.zeros(num_units))
+
+
+class AttnBlockpp(nn.Module):
+    """parameter holder for reference layerspp.py:72-101 (skip_rescale=True)"""
+
+    def __init__(self, channels, init_scale=0.0):
+        super().__init__()
+        self.GroupNorm_0 = nn.GroupNorm(min(channels // 4, 32), channels, eps=1e-6)
+        self.NIN_0 = NIN(channels, channels)
+        self.NIN_1 = NIN(channels, channels)
+        self.NIN_2 = NIN(channels, channels)
+        self.NIN_3 = NIN(channels, channels, init_scale=init_scale)
+        self.channels = channels
+
+
 class _Workspace:
     """Named device buffers with stable addresses (CUDA-graph friendly, no per-call allocation)."""
 
@@ -121,7 +149,6 @@ class NCSNpp(nn.Module):
         unsupported = []
         if nonlinearity != "swish": unsupported.append(f"nonlinearity={nonlinearity}")
         if any(r in list(attn_resolutions) for r in all_res): unsupported.append("attn_resolutions")
-        if bottleneck_attn: unsupported.append("bottleneck_attn=True")
         if not conditional: unsupported.append("conditional=False")
         if not fir or list(fir_kernel) != [1, 3, 3, 1]: unsupported.append("fir/fir_kernel")
         if not skip_rescale: unsupported.append("skip_rescale=False")
@@ -132,17 +159,22 @@ class NCSNpp(nn.Module):
         if embedding_type.lower() != "fourier": unsupported.append(f"embedding_type={embedding_type}")
         if dropout != 0.0: unsupported.append("dropout")
         if num_channels != 4: unsupported.append("num_channels")
-        if dict(output_layer_kwargs).get("kernel_size", 3) != 1 or dict(output_layer_kwargs).get("bias", False):
-            unsupported.append("output_layer_kwargs (need 1x1, no bias)")
+        olk = dict(output_layer_kwargs)
+        if (olk.get("kernel_size", 3) not in (1, 3) or olk.get("bias", False)
+                or olk.get("padding", "same") != "same" or olk.get("padding_mode", "zeros") != "zeros"):
+            unsupported.append("output_layer_kwargs (need kernel_size 1 or 3, no bias, zero 'same' padding)")
+        if nf % 8 or any((nf * m) % 8 for m in ch_mult): unsupported.append("channel counts must be multiples of 8")
         if unsupported:
             raise NotImplementedError(
-                "flowdec_b200.NCSNpp implements the FlowDec configuration family "
-                "(ncsnpp_final_no_attn.yaml); unsupported: " + ", ".join(unsupported))
+                "flowdec_b200.NCSNpp implements the configuration family of the reference's configs "
+                "(ncsnpp_final_no_attn.yaml, ncsnpp_default_ycond.yaml); unsupported: " + ", ".join(unsupported))
 
         self.nf, self.ch_mult, self.num_res_blocks = nf, ch_mult, num_res_blocks
         self.num_resolutions = len(ch_mult)
         self.image_size = image_size
-        self.output_layer = nn.Conv2d(num_channels, 2, kernel_size=1, bias=False)
+        self.bottleneck_attn = bool(bottleneck_attn)
+        self.out_k = int(olk.get("kernel_size", 3))
+        self.output_layer = nn.Conv2d(num_channels, 2, kernel_size=self.out_k, padding=self.out_k // 2, bias=False)
 
         # --- module list in the reference's construction order (ncsnpp.py:102-252) ---
         mods = [GaussianFourierProjection(embedding_size=nf, scale=fourier_scale),
@@ -162,6 +194,8 @@ class NCSNpp(nn.Module):
                 hs_c.append(in_ch)
         in_ch = hs_c[-1]
         mods.append(RB(in_ch=in_ch))
+        if self.bottleneck_attn:
+            mods.append(AttnBlockpp(in_ch, init_scale=init_scale))
         mods.append(RB(in_ch=in_ch))
         for lvl in reversed(range(self.num_resolutions)):
             for _ in range(num_res_blocks + 1):
@@ -177,8 +211,12 @@ class NCSNpp(nn.Module):
 
         self._prepared = None      # packed weights (built lazily, dropped on load_state_dict / .to())
         self._temb_cache = {}
-        self._workspaces = {}      # lane -> _Workspace (one per concurrently running micro-batch stream)
-        self._lane = 0
+        # (lane, B, F, T) -> _Workspace, least recently used first; signatures in `_pinned` (those of live CUDA
+        # graphs, set by FlowModel) are never evicted, others beyond `max_workspaces` are
+        self._workspaces = OrderedDict()
+        self._pinned = set()
+        self.max_workspaces = 4
+        self._ws_cur = None
         self.stats_slabs = 64
         self.fuse_stats = True     # GroupNorm partial sums produced by the conv epilogue
         self.pyramid_shift_after_gemm = True
@@ -201,26 +239,83 @@ class NCSNpp(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._invalidate()
-        self._workspaces = {}
+        self._workspaces = OrderedDict()
         return super()._apply(fn, *a, **k)
 
-    @property
-    def _ws(self):
-        w = self._workspaces.get(self._lane)
+    # ------------------------------------------------------------------ workspaces
+    def pin_workspaces(self, sigs):
+        """sigs: set of (micro-batch, F, T) whose workspaces must keep their addresses (captured CUDA graphs
+        replay into them); everything else becomes evictable"""
+        self._pinned = set(sigs)
+        self._evict()
+
+    def _evict(self):
+        free = [k for k in self._workspaces if k[1:] not in self._pinned and k != self._ws_cur]
+        while len(self._workspaces) > self.max_workspaces and free:
+            del self._workspaces[free.pop(0)]
+
+    def _select_ws(self, lane, B, Fq, T):
+        key = (lane, B, Fq, T)
+        self._ws_cur = key
+        w = self._workspaces.get(key)
         if w is None:
-            w = self._workspaces[self._lane] = _Workspace()
+            w = self._workspaces[key] = _Workspace()
+            self._evict()
+        else:
+            self._workspaces.move_to_end(key)
+        self._ws = w
         return w
+
+    def workspace_bytes(self):
+        return sum(w.nbytes() for w in self._workspaces.values())
 
     @staticmethod
     def _npad(cout):
-        if cout <= 16:
-            return 16
-        if cout in (128, 256):
-            return cout
-        raise NotImplementedError(f"tcgen05 conv tile for Cout={cout} not instantiated (16/128/256)")
+        """rows of the packed weight: the tcgen05 tiles take 128 / 256 output channels, every other width runs
+        on the shape-generic kernel, which needs no padding"""
+        return cout
+
+    # ------------------------------------------------------------------ structure walk
+    def _plan(self):
+        """Static walk of the network on channel counts only: for every res-block the channel split of its
+        (virtual concat) input.  Lets prepare() pack every fused conv1+skip and multi-source conv0 weight up
+        front, so no packing kernel runs inside velocity() (where lanes run on separate streams)."""
+        mods = self.all_modules
+        plan, idx = {}, 4
+        hs = [self.nf]
+        for lvl in range(self.num_resolutions):
+            for _ in range(self.num_res_blocks):
+                plan[idx] = [hs[-1]]
+                hs.append(mods[idx].out_ch)
+                idx += 1
+            if lvl != self.num_resolutions - 1:
+                plan[idx] = [hs[-1]]
+                idx += 2                      # down res-block + Combine
+                hs.append(mods[idx - 2].out_ch)
+        h = hs[-1]
+        plan[idx] = [h]
+        h = mods[idx].out_ch
+        idx += 1
+        if self.bottleneck_attn:
+            idx += 1
+        plan[idx] = [h]
+        h = mods[idx].out_ch
+        idx += 1
+        for lvl in reversed(range(self.num_resolutions)):
+            for _ in range(self.num_res_blocks + 1):
+                plan[idx] = [h, hs.pop()]
+                h = mods[idx].out_ch
+                idx += 1
+            idx += 2                          # GroupNorm + pyramid conv
+            if lvl != 0:
+                plan[idx] = [h]
+                h = mods[idx].out_ch
+                idx += 1
+        assert not hs and idx == len(mods)
+        return plan
 
     def prepare(self):
-        """Repack weights for the kernels (OIHW fp32 -> K-major bf16 [Npad, Ktot], fused skips)."""
+        """Repack weights for the kernels (OIHW fp32 -> K-major bf16 [rows, Ktot], fused skips)."""
         if self._prepared is not None:
             return self._prepared
         dev = self.output_layer.weight.device
@@ -228,6 +323,7 @@ class NCSNpp(nn.Module):
             raise RuntimeError("flowdec_b200.NCSNpp runs on CUDA (sm_100a) only; call .cuda() first")
         P = {}
         inv = 1.0 / math.sqrt(2.0)
+        plan = self._plan()
         with torch.no_grad():
             for i, m in enumerate(self.all_modules):
                 if isinstance(m, ResnetBlockBigGANpp):
@@ -251,6 +347,21 @@ class NCSNpp(nn.Module):
                     e["g1"], e["be1"] = m.GroupNorm_1.weight.float().contiguous(), m.GroupNorm_1.bias.float().contiguous()
                     e["dw"], e["db"] = m.Dense_0.weight.float().contiguous(), m.Dense_0.bias.float().contiguous()
                     P[i] = e
+                    # every variant velocity() will ask for (the splits are static)
+                    split = plan[i]
+                    self._skip_weight(e, [cin] if (m.up or m.down) else split, cout)
+                    if not (m.up or m.down):
+                        self._conv0_weight(e, split, cout)
+                elif isinstance(m, AttnBlockpp):
+                    C = m.channels
+                    wq = torch.cat([n.W.float().t() for n in (m.NIN_0, m.NIN_1, m.NIN_2)], 0).reshape(3 * C, C, 1, 1)
+                    eye = (torch.eye(C, device=dev) * inv).reshape(C, C, 1, 1)
+                    P[i] = dict(g=m.GroupNorm_0.weight.float().contiguous(), be=m.GroupNorm_0.bias.float().contiguous(),
+                                wqkv=ops.pack_conv_weight([(wq, 1)], 3 * C),
+                                bqkv=torch.cat([n.b.float() for n in (m.NIN_0, m.NIN_1, m.NIN_2)]).contiguous(),
+                                wo=ops.pack_conv_weight([((m.NIN_3.W.float().t() * inv).reshape(C, C, 1, 1), 1),
+                                                         (eye, 1)], C),
+                                bo=(m.NIN_3.b.float() * inv).contiguous())
                 elif isinstance(m, Combine):
                     P[i] = dict(w=m.Conv_0.weight.float().reshape(m.Conv_0.weight.shape[0], 4).contiguous(),
                                 b=m.Conv_0.bias.float().contiguous())
@@ -266,13 +377,16 @@ class NCSNpp(nn.Module):
             P["Wf"] = self.all_modules[0].W.float().contiguous()
             P["l1w"], P["l1b"] = self.all_modules[1].weight.float().contiguous(), self.all_modules[1].bias.float().contiguous()
             P["l2w"], P["l2b"] = self.all_modules[2].weight.float().contiguous(), self.all_modules[2].bias.float().contiguous()
-            wo = self.output_layer.weight.float().reshape(2, 4).cpu().contiguous()
-            P["w_out8"] = (ctypes.c_float * 8)(*wo.flatten().tolist())
+            if self.out_k == 1:
+                wo = self.output_layer.weight.float().reshape(2, 4).cpu().contiguous()
+                P["w_out8"] = (ctypes.c_float * 8)(*wo.flatten().tolist())
+            else:
+                P["w_out72"] = self.output_layer.weight.float().contiguous()      # [2,4,3,3] on the device
         self._prepared = P
         return P
 
     def _skip_weight(self, e, seg_channels, cout):
-        """packed [Npad, 9*cout + sum(seg)] weight of conv1 + 1x1 skip over the given source split"""
+        """packed [rows, 9*cout + sum(seg)] weight of conv1 + 1x1 skip over the given source split"""
         key = tuple(seg_channels)
         wp = e["w1_cache"].get(key)
         if wp is None:
@@ -282,6 +396,21 @@ class NCSNpp(nn.Module):
                 segs.append((e["w2_full"][:, c0:c0 + c].contiguous(), 1))
                 c0 += c
             assert c0 == e["w2_full"].shape[1]
+            wp = ops.pack_conv_weight(segs, self._npad(cout))
+            e["w1_cache"][key] = wp
+        return wp
+
+    def _conv0_weight(self, e, seg_channels, cout):
+        """Conv_0 packed for a multi-source (virtual concat) operand: K = segment > tap > channel"""
+        if len(seg_channels) == 1:
+            return e["w0"]
+        key = ("w0",) + tuple(seg_channels)
+        wp = e["w1_cache"].get(key)
+        if wp is None:
+            segs, c0 = [], 0
+            for c in seg_channels:
+                segs.append((e["w0_full"][:, c0:c0 + c].contiguous(), 9))
+                c0 += c
             wp = ops.pack_conv_weight(segs, self._npad(cout))
             e["w1_cache"][key] = wp
         return wp
@@ -307,10 +436,11 @@ class NCSNpp(nn.Module):
         for i, m in enumerate(self.all_modules):
             if isinstance(m, ResnetBlockBigGANpp):
                 e = P[i]
-                npad = self._npad(m.out_ch)
-                b = torch.zeros(npad, device=dev)
+                b = torch.zeros(self._npad(m.out_ch), device=dev)
                 ops.matvec(temb, e["dw"], e["db"], b, silu_in=True, add=e["b0"])
                 out[i] = b
+        if len(self._temb_cache) >= 256:      # e.g. a long run of N=50 Euler calls with changing grids
+            self._temb_cache.pop(next(iter(self._temb_cache)))
         self._temb_cache[key] = out
         return out
 
@@ -339,14 +469,35 @@ class NCSNpp(nn.Module):
         """a = FIR?(SiLU(GroupNorm(cat(srcs)))) as one bf16 NHWC tensor (+ FIR(cat(srcs)) if raw_name)."""
         B, H, W = srcs[0].shape[:3]
         C = sum(s.shape[3] for s in srcs)
-        parts = [self._partials(s, scache) for s in srcs]
-        ss = self._ws.get("gn_ss", (B, C, 2), torch.float32, srcs[0].device)
-        ops.gn_finalize(parts, [s.shape[3] for s in srcs], H * W, gamma, beta, min(C // 4, 32), 1e-6, ss)
+        ss = self._gn_scale_shift(srcs, gamma, beta, scache, "gn_ss")
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
         a = self._ws.get(name, (B, Ho, Wo, C), torch.bfloat16, srcs[0].device)
         raw = self._ws.get(raw_name, (B, Ho, Wo, C), torch.bfloat16, srcs[0].device) if raw_name else None
         ops.gn_act_resample(srcs, ss, a, mode, out_raw=raw)
         return (a, raw) if raw_name else a
+
+    def _conv(self, srcs, wp, bias, out, stats_name=None, algo_k=None, scache=None):
+        """One convolution over the virtual concat `srcs` -> `out` (bf16 NHWC): tcgen05 tiles when the shape
+        fits, the shape-generic kernel otherwise.  With `stats_name` the tensor-core epilogue also emits the
+        GroupNorm partial sums of the output (registered in `scache`); the generic path leaves them to an
+        on-demand fd_chan_stats pass."""
+        B, H, W, cout = out.shape
+        if scache is not None:
+            scache.pop(out.data_ptr(), None)
+        if ops.tensor_conv_ok(B, H, W, wp.shape[0], [s[2] for s in srcs]) and \
+                (all(len(s) <= 4 or s[4] is None for s in srcs) or ops.halo_eligible(B, H, W, wp.shape[0])):
+            st = None
+            if self.fuse_stats and stats_name is not None:
+                S = ops.conv_stats_slabs(H, W)
+                # large S: shared scratch, compacted below into a per-tensor buffer; small S: kept as is
+                st = self._ws.get("conv_stats" if S > self.stats_slabs else stats_name, (B, S, cout, 2),
+                                  torch.float32, out.device)
+            ops.conv_igemm(srcs, wp, bias, out, self.max_ctas, algo_k=algo_k, stats=st)
+            if st is not None:
+                scache[out.data_ptr()] = self._compact_stats(st, stats_name)
+        else:
+            ops.conv_direct(srcs, wp, bias, out)
+        return out
 
     def _resblock(self, i, srcs, tb, scache, want_stats=True):
         """reference layerspp.py:252-284; srcs = virtual concat of bf16 NHWC tensors."""
@@ -357,71 +508,54 @@ class NCSNpp(nn.Module):
         mode = 1 if m.down else (2 if m.up else 0)
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
         cin, cout = m.in_ch, m.out_ch
-        assert sum(s.shape[3] for s in srcs) == cin
-        # GroupNorm+SiLU fused into the conv's operand path (halo kernel) when the tile geometry allows;
-        # otherwise (and for the FIR-resampled conv0 input) a materialised bf16 activation tensor
-        fuse = self.fuse_gn_into_conv and ops.halo_eligible(B, Ho, Wo, self._npad(cout))
+        seg = [s.shape[3] for s in srcs]
+        assert sum(seg) == cin
+        # GroupNorm+SiLU applied inside the conv (halo kernel's operand transform, or on load in the generic
+        # kernel) when possible; otherwise (and for the FIR-resampled conv0 input) a materialised bf16 tensor
+        tensor0 = ops.tensor_conv_ok(B, Ho, Wo, self._npad(cout), seg if mode == 0 else [cin])
+        tensor1 = ops.tensor_conv_ok(B, Ho, Wo, self._npad(cout), [cout] + (seg if mode == 0 else [cin]))
+        halo = self.fuse_gn_into_conv and ops.halo_eligible(B, Ho, Wo, self._npad(cout))
         if mode != 0:
             a0, xr = self._gn_act(srcs, e["g0"], e["be0"], mode, scache, "act", raw_name="xr")
             conv0_srcs, w0 = [(a0, 0, cin, 9)], e["w0"]
-        elif fuse:
+        elif halo or not tensor0:
             ss0 = self._gn_scale_shift(srcs, e["g0"], e["be0"], scache, "gn_ss0")
             conv0_srcs, off = [], 0
             for sx in srcs:
                 conv0_srcs.append((sx, 0, sx.shape[3], 9, ss0, off))
                 off += sx.shape[3]
-            w0 = self._conv0_weight(e, [sx.shape[3] for sx in srcs], cout)
+            w0 = self._conv0_weight(e, seg, cout)
         else:
             a0 = self._gn_act(srcs, e["g0"], e["be0"], mode, scache, "act")
             conv0_srcs, w0 = [(a0, 0, cin, 9)], e["w0"]
         h1 = self._ws.get("h1", (B, Ho, Wo, cout), torch.bfloat16, dev)
-        scache.pop(h1.data_ptr(), None)
-        st_h1 = None
-        if self.fuse_stats:
-            st_h1 = self._ws.get("h1_stats", (B, ops.conv_stats_slabs(Ho, Wo), cout, 2), torch.float32, dev)
-        ops.conv_igemm(conv0_srcs, w0, tb[i], h1, self.max_ctas, stats=st_h1)
-        if st_h1 is not None:
-            scache[h1.data_ptr()] = self._compact_stats(st_h1, "h1_stats_c")
-        if fuse:
+        self._conv(conv0_srcs, w0, tb[i], h1, stats_name="h1_stats_c", scache=scache)
+        if halo or not tensor1:
             ss1 = self._gn_scale_shift([h1], e["g1"], e["be1"], scache, "gn_ss1")
             conv1_main = (h1, 0, cout, 9, ss1, 0)
         else:
             conv1_main = (self._gn_act([h1], e["g1"], e["be1"], 0, scache, "act"), 0, cout, 9)
         scache.pop(h1.data_ptr(), None)
-        if mode != 0:
-            skip = [xr]
-        else:
-            skip = list(srcs)
+        skip = [xr] if mode != 0 else list(srcs)
         wp = self._skip_weight(e, [s.shape[3] for s in skip], cout)
         out = self._ws.get(f"rb{i}", (B, Ho, Wo, cout), torch.bfloat16, dev)
         algo_k = 9 * cout + (cin if hasattr(m, "Conv_2") else 0)
-        scache.pop(out.data_ptr(), None)
-        st_out = None
-        if self.fuse_stats and want_stats:
-            S = ops.conv_stats_slabs(Ho, Wo)
-            # large S: shared scratch, compacted below into a per-block buffer; small S: kept as is
-            st_out = self._ws.get("rb_stats" if S > self.stats_slabs else f"rb{i}_stats_c", (B, S, cout, 2),
-                                  torch.float32, dev)
-        ops.conv_igemm([conv1_main] + [(s, 0, s.shape[3], 1) for s in skip], wp, e["b1"], out,
-                       self.max_ctas, algo_k=algo_k, stats=st_out)
-        if st_out is not None:
-            scache[out.data_ptr()] = self._compact_stats(st_out, f"rb{i}_stats_c")
+        self._conv([conv1_main] + [(s, 0, s.shape[3], 1) for s in skip], wp, e["b1"], out,
+                   stats_name=f"rb{i}_stats_c" if want_stats else None, algo_k=algo_k, scache=scache)
         return out
 
-    def _conv0_weight(self, e, seg_channels, cout):
-        """Conv_0 packed for a multi-source (virtual concat) operand: K = segment > tap > channel"""
-        if len(seg_channels) == 1:
-            return e["w0"]
-        key = ("w0",) + tuple(seg_channels)
-        wp = e["w1_cache"].get(key)
-        if wp is None:
-            segs, c0 = [], 0
-            for c in seg_channels:
-                segs.append((e["w0_full"][:, c0:c0 + c].contiguous(), 9))
-                c0 += c
-            wp = ops.pack_conv_weight(segs, self._npad(cout))
-            e["w1_cache"][key] = wp
-        return wp
+    def _attn(self, i, h, scache):
+        """reference layerspp.py:72-101 (AttnBlockpp, skip_rescale): GroupNorm -> q, k, v (NIN) -> softmax over
+        all H*W positions -> NIN -> (x + h)/sqrt(2); the residual rides as an identity K segment of the last conv"""
+        e = self._prepared[i]
+        B, H, W, C = h.shape
+        ss = self._gn_scale_shift([h], e["g"], e["be"], scache, "attn_ss")
+        qkv = self._ws.get("attn_qkv", (B, H, W, 3 * C), torch.float32, h.device)
+        ops.conv_direct([(h, 0, C, 1, ss, 0)], e["wqkv"], e["bqkv"], qkv, affine_only=True)
+        a = ops.attention(qkv, self._ws.get("attn_a", (B, H, W, C), torch.bfloat16, h.device))
+        out = self._ws.get(f"attn{i}", (B, H, W, C), torch.bfloat16, h.device)
+        scache.pop(out.data_ptr(), None)
+        return ops.conv_direct([(a, 0, C, 1), (h, 0, C, 1)], e["wo"], e["bo"], out)
 
     def _compact_stats(self, st, name):
         """conv-epilogue partials [B,S,C,2] -> at most `stats_slabs` slabs (coalesced stage-1 reduce)"""
@@ -438,13 +572,13 @@ class NCSNpp(nn.Module):
         out = c1*base1 + c2*base2 + c3*base3 + coef*v.  x, y, bases, out: fp32 [B,F,T,2] (= complex64 [B,F,T])."""
         P = self.prepare()
         tb = self.temb_biases(t)
-        self._lane = lane            # selects the workspace: lanes may run concurrently on different streams
-        ws, dev = self._ws, x.device
         B, Fq, T = x.shape[0], x.shape[1], x.shape[2]
         nres = self.num_resolutions
-        if Fq % (16 << (nres - 1)) or T % (8 << (nres - 1)):
-            raise ValueError(f"spectrogram {Fq}x{T} is not tileable for {nres} resolutions "
-                             "(need F % (16*2^(L-1)) == 0 and T % (8*2^(L-1)) == 0; pad_spec pads T to 64)")
+        if Fq % (1 << (nres - 1)) or T % (1 << (nres - 1)):
+            raise ValueError(f"spectrogram {Fq}x{T} cannot be halved {nres - 1} times "
+                             "(pad_spec pads T to a multiple of 64)")
+        # lanes may run concurrently on different streams: one workspace per (lane, shape)
+        ws, dev = self._select_ws(lane, B, Fq, T), x.device
         scache = {}
         self._stat_counter = 0
         mods = self.all_modules
@@ -470,6 +604,9 @@ class NCSNpp(nn.Module):
         h = hs[-1]
         h = self._resblock(idx, [h], tb, scache)
         idx += 1
+        if self.bottleneck_attn:
+            h = self._attn(idx, h, scache)
+            idx += 1
         h = self._resblock(idx, [h], tb, scache)
         idx += 1
         pyramid = None
@@ -478,19 +615,24 @@ class NCSNpp(nn.Module):
                 h = self._resblock(idx, [h, hs.pop()], tb, scache)
                 idx += 1
             g = P[idx]
-            a = self._gn_act([h], g["g"], g["b"], 0, scache, "act")
             idx += 1
             pc = P[idx]
+            C = h.shape[3]
             ph = ws.get(f"pyr_out{lvl}", (B, H, W, 4), torch.float32, dev)
-            if self.pyramid_shift_after_gemm:
+            if self.pyramid_shift_after_gemm and ops.tensor_conv_ok(B, H, W, 48, [C], out_f32=True):
                 # one pass over `a`: 36 per-tap products per pixel on tensor cores, then a gather-sum
+                a = self._gn_act([h], g["g"], g["b"], 0, scache, "act")
                 part = ws.get("pyr_part", (B, H, W, 36), torch.float32, dev)
-                ops.conv_igemm([(a, 0, a.shape[3], 1)], pc["wt"], None, part, self.max_ctas,
-                               algo_k=9 * a.shape[3], algo_cout=4)
+                ops.conv_igemm([(a, 0, C, 1)], pc["wt"], None, part, self.max_ctas, algo_k=9 * C, algo_cout=4)
                 ops.pyramid_gather(part, pc["b4"], pyramid, ph)
                 pyramid = ph
             else:
-                ops.conv_igemm([(a, 0, a.shape[3], 9)], pc["w"], pc["b"], ph, self.max_ctas)
+                if ops.tensor_conv_ok(B, H, W, 16, [C], out_f32=True):
+                    a = self._gn_act([h], g["g"], g["b"], 0, scache, "act")
+                    ops.conv_igemm([(a, 0, C, 9)], pc["w"], pc["b"], ph, self.max_ctas)
+                else:
+                    ss = self._gn_scale_shift([h], g["g"], g["b"], scache, "gn_ss")
+                    ops.conv_direct([(h, 0, C, 9, ss, 0)], pc["w"], pc["b"], ph, cout=4)
                 pyramid = ph if pyramid is None else ops.pyramid_up_add(pyramid, ph, ph)
             idx += 1
             if lvl != 0:
@@ -500,10 +642,18 @@ class NCSNpp(nn.Module):
         assert not hs and idx == len(mods)
         if out is None and v_out is None:
             v_out = torch.empty(B, Fq, T, 2, device=dev, dtype=torch.float32)
-        ops.output_axpy(pyramid, P["w_out8"], base1, c1, base2, c2, coef, out, v_out, base3=base3, c3=c3)
+        if self.out_k == 1:
+            ops.output_axpy(pyramid, P["w_out8"], base1, c1, base2, c2, coef, out, v_out, base3=base3, c3=c3)
+        else:
+            ops.output_conv3_axpy(pyramid, P["w_out72"], base1, c1, base2, c2, coef, out, v_out, base3=base3, c3=c3)
         return out if out is not None else v_out
 
+    @torch.no_grad()
     def forward(self, x, y, t):
+        with torch.cuda.device(x.device):
+            return self._forward(x, y, t)
+
+    def _forward(self, x, y, t):
         """x, y: complex64 [B,1,F,T]; t: float tensor with one element (the reference passes a
         shared scalar time, model.py:470-474).  Returns complex64 [B,1,F,T]."""
         if torch.is_tensor(t):

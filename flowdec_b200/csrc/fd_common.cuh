@@ -17,6 +17,7 @@ namespace fd {
 // ----------------------------------------------------------------------------
 // error reporting shared by every C-ABI entry point (see include/flowdec_b200.h)
 // ----------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);
 

@@ -842,14 +842,18 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// per-device caches (a process may drive several GPUs: `enhance.py --device cuda:1`)
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 int device_sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sms;
+  static int sms[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
 }
 
 // NHWC bf16 tensor [B,H,W,Ctot]; the map exposes channels [c_begin, c_begin + c_count)
@@ -893,12 +897,13 @@ template <int N, bool OUT_F32, bool CTA2>
 static int launch_conv(const ConvParams& p, int max_ctas, cudaStream_t stream) {
   auto kern = conv_igemm_kernel<N, OUT_F32, CTA2>;
   using Cfg = ConvCfg<N, CTA2>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};   // function attributes are per device
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     FD_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
                cudaGetErrorString(e));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   int grid = std::min(p.num_tiles, max_ctas > 0 ? max_ctas : device_sm_count());
   if (CTA2) grid &= ~1;
@@ -924,12 +929,13 @@ template <int N, bool XF>
 static int launch_halo(const HaloParams& p, int max_ctas, cudaStream_t stream) {
   auto kern = conv_halo_kernel<N, XF>;
   using Cfg = HaloCfg<N>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};   // function attributes are per device
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     FD_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
                cudaGetErrorString(e));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   int grid = std::min(p.num_tiles, max_ctas > 0 ? max_ctas : device_sm_count()) & ~1;
   cudaLaunchConfig_t cfg;

@@ -314,6 +314,7 @@ bool fir_tiles_eligible(int C1, int C2, int H, int W, int mode) {
 }
 
 int device_sm_count();
+int current_device();
 
 int fir_tiles_launch(const void* src1, int C1, const void* src2, int C2, const float* scale_shift, void* out,
                      void* out_raw, int B, int H, int W, int mode, cudaStream_t stream) {
@@ -335,7 +336,8 @@ int fir_tiles_launch(const void* src1, int C1, const void* src2, int C2, const f
   p.scale_shift = scale_shift;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.out_raw = static_cast<__nv_bfloat16*>(out_raw);
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {false};   // function attributes are per device
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(fir_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmem);
     cudaError_t e2 = cudaFuncSetAttribute(fir_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmem);

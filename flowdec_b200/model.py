@@ -8,6 +8,8 @@ state_dict keys.  No lightning / hydra / torchdyn / torchcfm dependency: the ODE
 fused kernel launches (flowdec_b200/sampling/solvers.py), optionally captured as one CUDA graph
 per (batch, length, N, solver).
 """
+import functools
+from collections import OrderedDict
 from typing import Optional
 
 import numpy as np
@@ -17,6 +19,20 @@ import torch.nn as nn
 from . import ops
 from .sampling.solvers import get_solver, stages, t_grid
 from .util.other import padded_frames
+
+
+def _on_model_device(fn):
+    """Run a method with the model's GPU as the current CUDA device: the ctypes launches, the tensor-map
+    encoder and torch.cuda.current_stream() all act on the *current* device, which need not be the model's
+    (reference CLI: `enhance.py --device cuda:1`)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        dev = self.device
+        if dev.type != "cuda":
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 class EnhancementModel(nn.Module):
@@ -49,11 +65,28 @@ class EnhancementModel(nn.Module):
     def load_from_checkpoint(cls, checkpoint_path, map_location=None, ema=True, build_fn=None, **kwargs):
         """What the reference intends (model.py:352-385, commented out there): build the model, then
         load `_pl_ema_state_dict` (ema=True) or `state_dict`.  Hydra is not a dependency here, so the
-        model comes from `build_fn()` (default: the shipped flowdec_75m configuration)."""
-        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
-        model = build_fn() if build_fn is not None else build_flowdec("75m")
-        sd = ckpt["_pl_ema_state_dict"] if ema else ckpt["state_dict"]
-        model.load_state_dict(sd, strict=False)
+        model comes from `build_fn()` (default: the shipped flowdec_75m configuration, or the ScoreDec
+        baseline when called on ScoreModel).  A checkpoint whose backbone / feature-extractor keys do not
+        match the model raises instead of silently leaving random weights in place."""
+        try:
+            ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=True)
+        except Exception:    # Lightning checkpoints pickle hyper-parameter objects next to the tensors
+            ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        if build_fn is not None:
+            model = build_fn()
+        else:
+            model = build_scoredec() if issubclass(cls, ScoreModel) else build_flowdec("75m")
+        key = "_pl_ema_state_dict" if ema else "state_dict"
+        if key not in ckpt:
+            raise KeyError(f"{checkpoint_path}: no '{key}' entry (keys: {sorted(ckpt)[:8]})")
+        res = model.load_state_dict(ckpt[key], strict=False)
+        tolerated = ("sigma_x", "sigma_y")     # absent from ScoreDec / older checkpoints
+        missing = [k for k in res.missing_keys if k not in tolerated]
+        unexpected = [k for k in res.unexpected_keys if k not in tolerated]
+        if missing or unexpected:
+            raise RuntimeError(f"{checkpoint_path} does not match {type(model).__name__}: "
+                               f"{len(missing)} missing keys (e.g. {missing[:3]}), "
+                               f"{len(unexpected)} unexpected keys (e.g. {unexpected[:3]})")
         return model
 
 
@@ -68,7 +101,10 @@ class FlowModel(EnhancementModel):
             raise NotImplementedError("callable sigma_x / sigma_y (reference model.py:407-419) is a training-time option")
         self.sigma_x = nn.Parameter(as_t(sigma_x), requires_grad=False)
         self.sigma_y = nn.Parameter(as_t(sigma_y), requires_grad=False)
-        self._graphs = {}
+        # static buffers + CUDA graph per (batch, padded-frame bucket, N, solver, sigma_fac); least recently
+        # used entries (and the backbone workspaces only they used) are dropped beyond `graph_cache_size`
+        self._graphs = OrderedDict()
+        self.graph_cache_size = 4
         self.use_cuda_graph = True
         self.max_batch = 16         # clips per backbone pass (micro-batch); 16 x 2 s = 8 x 4 s = 4096 frames
         self.max_frames_per_pass = 4096   # padded STFT frames per backbone pass (8 clips x 4 s)
@@ -76,14 +112,19 @@ class FlowModel(EnhancementModel):
         self._streams = []
         self._sig_cache = None
 
-    def _apply(self, fn, *a, **k):
-        self._graphs = {}
+    def _drop_graphs(self):
+        self._graphs = OrderedDict()
         self._sig_cache = None
+        if hasattr(self.backbone, "pin_workspaces"):
+            self.backbone.pin_workspaces(set())
+
+    def _apply(self, fn, *a, **k):
+        self._drop_graphs()
+        self._streams = []
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict=None, **kw):
-        self._graphs = {}
-        self._sig_cache = None
+        self._drop_graphs()
         return super().load_state_dict(state_dict, strict=self.strict_loading if strict is None else strict, **kw)
 
     # ------------------------------------------------------------------------------------
@@ -97,6 +138,10 @@ class FlowModel(EnhancementModel):
         that long clips (the reference CLI accepts up to 30 s, enhance.py:115) keep the activation
         workspace at the size it has for 8 x 4 s"""
         return max(1, min(self.max_batch, self.max_frames_per_pass // max(Tp, 1)))
+
+    def _chunks(self, B, Tp):
+        mb = self._micro_batch(Tp)
+        return [(lo, min(B, lo + mb)) for lo in range(0, B, mb)]
 
     def _side_streams(self, n):
         while len(self._streams) < n:
@@ -122,25 +167,25 @@ class FlowModel(EnhancementModel):
         """All device work of enhance() on static buffers `st` (graph-capturable)."""
         fe, bb = self.feature_extractor, self.backbone
         B, L, Tp = st["B"], st["L"], st["Tp"]
-        lens = st.get("len")          # int32 [B] for ragged (length-bucketed) batches, else None
+        lens = st["len"]              # int32 [B]: per-clip sample counts (rows of pitch L = Tp*384)
         ops.normfac(st["y"], 1 if self.normalize_mode == "noisy" else 0, st["nf"], lengths=lens)
         fe.stft_compress(st["y"], st["nf"], st["Y"], lengths=lens)
         ops.x0_noise(st["Y"], self._sigma_vec(768), st["eps"], sigma_fac, st["x"][0])
         cur = 0
-        traj = [st["x"][0]] if want_traj else None
-        # weights / time-embedding biases are produced on this stream before any lane forks
+        traj = [st["x"][0].clone()] if want_traj else None
+        # packed weights (every fused-skip / multi-source variant) and the time-embedding biases are produced
+        # on this stream BEFORE any lane forks: side lanes only ever read them
         bb.prepare()
         for (t, dt) in t_grid(N):
             for stage in stages(solver, t, dt):
                 bb.temb_biases(float(stage[0]))
+        chunks = self._chunks(B, Tp)
+        nlanes = max(1, min(self.overlap_streams, len(chunks)))
         for (t, dt) in t_grid(N):
             bufs = {"x": st["x"][cur], "xn": st["x"][cur ^ 1], "tmp": st["tmp"]}
             for (te, src, dst, b1, c1, b2, c2, coef) in stages(solver, t, dt):
                 # micro-batches are independent: alternate them over `overlap_streams` CUDA streams so
                 # the HBM-bound GroupNorm/FIR passes of one overlap the tensor-bound convs of another
-                mb = self._micro_batch(Tp)
-                chunks = [(lo, min(B, lo + mb)) for lo in range(0, B, mb)]
-                nlanes = max(1, min(self.overlap_streams, len(chunks)))
                 main = torch.cuda.current_stream()
                 lanes = [main] + self._side_streams(nlanes - 1)
                 for s_ in lanes[1:]:
@@ -154,24 +199,78 @@ class FlowModel(EnhancementModel):
                     main.wait_stream(s_)
             cur ^= 1
             if want_traj:
-                keep = torch.empty_like(st["x"][cur])
-                keep.copy_(st["x"][cur])
-                traj.append(keep)
+                traj.append(st["x"][cur].clone())
         fe.istft_decompress(st["x"][cur], L, st["nf"], st["out"], lengths=lens)
         return traj
 
-    def _static(self, B, L, dev, Tp=None):
-        ragged = Tp is not None       # ragged bucket: rows of pitch L = Tp*384 hold clips of individual lengths
-        if Tp is None:
-            Tp = padded_frames(1 + L // 384)
+    def _static(self, B, Tp, dev):
+        """static buffers of one (batch, padded-frame bucket): waveform rows have pitch Tp*384 >= any clip length
+        of the bucket, so every L that pads to Tp frames shares the entry (and its captured graph)"""
+        L = Tp * 384
         f32 = dict(device=dev, dtype=torch.float32)
-        extra = dict(len=torch.empty(B, device=dev, dtype=torch.int32)) if ragged else {}
-        return dict(B=B, L=L, Tp=Tp, y=torch.empty(B, L, **f32), nf=torch.empty(B, **f32), **extra,
+        return dict(B=B, L=L, Tp=Tp, y=torch.zeros(B, L, **f32), nf=torch.empty(B, **f32),
+                    len=torch.empty(B, device=dev, dtype=torch.int32),
                     Y=torch.empty(B, 768, Tp, 2, **f32), eps=torch.empty(B, 768, Tp, 2, **f32),
                     x=[torch.empty(B, 768, Tp, 2, **f32) for _ in range(2)],
                     tmp=torch.empty(B, 768, Tp, 2, **f32), out=torch.empty(B, L, **f32))
 
+    def _entry(self, B, Tp, N, solver, sigma_fac, dev):
+        key = (B, Tp, int(N), solver, float(sigma_fac))
+        entry = self._graphs.get(key)
+        if entry is None:
+            while len(self._graphs) >= max(1, self.graph_cache_size):
+                self._graphs.popitem(last=False)
+            entry = dict(st=self._static(B, Tp, dev), graph=None, warm=0,
+                         sigs={(hi - lo, 768, Tp) for lo, hi in self._chunks(B, Tp)})
+            self._graphs[key] = entry
+            if hasattr(self.backbone, "pin_workspaces"):
+                # workspaces of evicted entries become collectable; live graphs keep theirs (stable addresses)
+                self.backbone.pin_workspaces(set().union(*[e["sigs"] for e in self._graphs.values()]))
+        else:
+            self._graphs.move_to_end(key)
+        return entry
+
+    def _enhance_bucket(self, y2d, lens, N, solver, sigma_fac, noise, want_traj):
+        """y2d: [B, Lin] (host or device) whose row b holds lens[b] valid samples; all clips share one
+        padded-frame bucket.  Returns the static-buffer dict (st["out"][b, :lens[b]] is the enhanced clip)
+        and the trajectory (or None)."""
+        dev = self.device
+        B, Lin = y2d.shape
+        Tp = padded_frames(1 + max(lens) // 384)
+        entry = self._entry(B, Tp, N, solver, sigma_fac, dev)
+        st = entry["st"]
+        n_copy = min(Lin, st["L"])
+        if entry.get("filled", 0) > n_copy:
+            st["y"][:, n_copy:entry["filled"]].zero_()      # a longer clip of the bucket was here before
+        entry["filled"] = n_copy
+        st["y"][:, :n_copy].copy_(y2d[:, :n_copy], non_blocking=True)
+        st["len"].copy_(torch.tensor(lens, dtype=torch.int32), non_blocking=True)
+        if noise is None:
+            eps = torch.randn(B, 768, Tp, dtype=torch.complex64, device=dev)
+        else:
+            eps = noise.to(dev, torch.complex64).reshape(B, 768, Tp)
+        st["eps"].copy_(torch.view_as_real(eps))
+        traj = None
+        if want_traj or not self.use_cuda_graph:
+            traj = self._run(st, N, solver, sigma_fac, want_traj)
+        elif entry["graph"] is None:
+            # first call: eager (also builds packed weights / time-embedding caches); second: capture
+            if entry["warm"] == 0:
+                self._run(st, N, solver, sigma_fac, False)
+                entry["warm"] = 1
+            else:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._run(st, N, solver, sigma_fac, False)
+                entry["graph"] = g
+                g.replay()
+        else:
+            entry["graph"].replay()
+        return st, traj
+
     @torch.no_grad()
+    @_on_model_device
     def enhance(self, y, return_preprocess_info: bool = False, N: int = 50, solver: str = "euler",
                 with_grad: bool = False, sigma_fac: float = 1.0, return_traj: bool = False,
                 noise: Optional[torch.Tensor] = None, lengths=None, **kwargs):
@@ -200,36 +299,8 @@ class FlowModel(EnhancementModel):
         B, C, L = y.shape
         if L <= 767:
             raise ValueError(f"waveform length {L} must exceed the STFT reflect pad (767)")
-        key = (B * C, L, int(N), solver, float(sigma_fac))
-        entry = self._graphs.get(key)
-        if entry is None:
-            entry = dict(st=self._static(B * C, L, dev), graph=None, warm=0)
-            self._graphs[key] = entry
-        st = entry["st"]
-        st["y"].copy_(y.reshape(B * C, L), non_blocking=True)
-        if noise is None:
-            eps = torch.randn(B, C, 768, st["Tp"], dtype=torch.complex64, device=dev)
-        else:
-            eps = noise.to(dev, torch.complex64)
-        st["eps"].copy_(torch.view_as_real(eps.reshape(B * C, 768, st["Tp"])))
-        traj = None
-        if return_traj or not self.use_cuda_graph:
-            traj = self._run(st, N, solver, sigma_fac, return_traj)
-        elif entry["graph"] is None:
-            # first call: eager (also builds packed weights / time-embedding caches); second: capture
-            if entry["warm"] == 0:
-                self._run(st, N, solver, sigma_fac, False)
-                entry["warm"] = 1
-            else:
-                g = torch.cuda.CUDAGraph()
-                torch.cuda.synchronize()
-                with torch.cuda.graph(g):
-                    self._run(st, N, solver, sigma_fac, False)
-                entry["graph"] = g
-                g.replay()
-        else:
-            entry["graph"].replay()
-
+        st, traj = self._enhance_bucket(y.reshape(B * C, L), [L] * (B * C), N, solver, sigma_fac, noise, return_traj)
+        Tp = st["Tp"]
         info = dict(orig_length=L, normfac=st["nf"].clone().reshape(B, C, 1) if C == 1 else st["nf"].clone(),
                     undo_pad_fn=(lambda Y_, T=1 + L // 384: Y_[..., :T]), squeeze_dims=squeeze_dims)
         if return_traj:
@@ -238,18 +309,17 @@ class FlowModel(EnhancementModel):
             for X in traj:
                 w = torch.empty(B * C, L, device=dev, dtype=torch.float32)
                 fe.istft_decompress(X, L, st["nf"], w)
-                X_hats.append(torch.view_as_complex(X.clone()).reshape(B, C, 768, st["Tp"]))
+                X_hats.append(torch.view_as_complex(X).reshape(B, C, 768, Tp))
                 xw = w.reshape(B, C, L)
                 for _ in range(squeeze_dims):
                     xw = xw.squeeze(0)
                 x_hats.append(xw)
             return torch.stack(X_hats), x_hats
-        x_hat = st["out"].clone().reshape(B, C, L)
+        x_hat = st["out"][:, :L].clone().reshape(B, C, L)
         for _ in range(squeeze_dims):
             x_hat = x_hat.squeeze(0)
         x_hat = x_hat.to(y_in.device)
         return (x_hat, info) if return_preprocess_info else x_hat
-
 
     def _enhance_ragged(self, y, lengths, N, solver, sigma_fac, noise, return_preprocess_info, return_traj):
         """length-bucketed batch: see enhance(lengths=)"""
@@ -273,39 +343,7 @@ class FlowModel(EnhancementModel):
                              "use flowdec_b200.batching.enhance_list to bucket a list of clips")
         if dev.type != "cuda":
             raise RuntimeError("flowdec_b200 runs on CUDA (sm_100a) only; call model.cuda()")
-        Tp = buckets.pop()
-        pitch = Tp * 384
-        key = ("ragged", B, Tp, int(N), solver, float(sigma_fac))
-        entry = self._graphs.get(key)
-        if entry is None:
-            entry = dict(st=self._static(B, pitch, dev, Tp=Tp), graph=None, warm=0)
-            self._graphs[key] = entry
-        st = entry["st"]
-        n_copy = min(Lin, pitch)
-        if n_copy < pitch:
-            st["y"][:, n_copy:].zero_()
-        st["y"][:, :n_copy].copy_(y.reshape(B, Lin)[:, :n_copy], non_blocking=True)
-        st["len"].copy_(torch.tensor(lens, dtype=torch.int32), non_blocking=True)
-        if noise is None:
-            eps = torch.randn(B, 1, 768, Tp, dtype=torch.complex64, device=dev)
-        else:
-            eps = noise.to(dev, torch.complex64)
-        st["eps"].copy_(torch.view_as_real(eps.reshape(B, 768, Tp)))
-        if not self.use_cuda_graph:
-            self._run(st, N, solver, sigma_fac, False)
-        elif entry["graph"] is None:
-            if entry["warm"] == 0:
-                self._run(st, N, solver, sigma_fac, False)
-                entry["warm"] = 1
-            else:
-                g = torch.cuda.CUDAGraph()
-                torch.cuda.synchronize()
-                with torch.cuda.graph(g):
-                    self._run(st, N, solver, sigma_fac, False)
-                entry["graph"] = g
-                g.replay()
-        else:
-            entry["graph"].replay()
+        st, _ = self._enhance_bucket(y.reshape(B, Lin), lens, N, solver, sigma_fac, noise, False)
         Lmax = max(lens)
         x_hat = st["out"][:, :Lmax].clone().reshape(B, 1, Lmax).to(y.device)
         if not return_preprocess_info:
@@ -339,6 +377,7 @@ class ScoreModel(EnhancementModel):
         return -self.backbone(xt, y, t_batch) / std
 
     @torch.no_grad()
+    @_on_model_device
     def enhance(self, y, sampler_type="pc", predictor="reverse_diffusion", corrector="ald", N=30,
                 corrector_steps=1, snr=0.5, return_preprocess_info=False, denoise=True,
                 probability_flow=False, noise=None, **kwargs):
@@ -387,11 +426,12 @@ class ScoreModel(EnhancementModel):
                             base2=Y[lo:hi], c2=c2, base3=base3[lo:hi] if base3 is not None else None,
                             c3=c3, coef=coef)
 
-        # prior: x_T = y + z * std(T)     (sdes.py:201-206)
+        # prior: x_T = y + z * std(T)     (sdes.py:201-206); x0_kernel with a unit sigma vector is out = Y + fac*z
         x = torch.empty_like(Y)
         xn = torch.empty_like(Y)
         x_mean = torch.empty_like(Y)
-        x.copy_(Y + draw() * float(sde._std(1.0)))
+        ones64 = torch.ones(768, device=dev, dtype=torch.float64)
+        ops.x0_noise(Y, ones64, draw(), float(sde._std(1.0)), x)
         timesteps = torch.linspace(sde.T, self.t_eps, N).numpy()
         for i in range(N):
             t = timesteps[i]
@@ -410,7 +450,7 @@ class ScoreModel(EnhancementModel):
             if last:
                 backbone_stage(x, t, x_mean, 1.0 + th_dt, -th_dt, None, 0.0, -G * G / std)
                 if not denoise:
-                    x_mean = x_mean + G * z
+                    ops.x0_noise(x_mean, ones64, z, G, x_mean)
             else:
                 backbone_stage(x, t, xn, 1.0 + th_dt, -th_dt, z, G, -G * G / std)
                 x, xn = xn, x

@@ -38,6 +38,7 @@ class _Quantizer:
         """codes int64 [B, n_q, T] -> (z_q [B, D, T], None, codes); reference call site demo.ipynb:104."""
         o = self._o
         o._require_cuda()
+        torch.cuda.set_device(o.device)
         codes = codes.to(o.device, torch.int64).contiguous()
         B, nq, T = codes.shape
         if nq > o.n_codebooks:
@@ -56,6 +57,7 @@ class _Quantizer:
         o._require_cuda()
         if o.in_proj_w is None:
             raise RuntimeError("this checkpoint has no quantizer in_proj weights (decode-only state_dict)")
+        torch.cuda.set_device(o.device)
         z = z.to(o.device, torch.float32).contiguous()
         B, D, T = z.shape
         if D != o.latent_dim:
@@ -112,8 +114,11 @@ class DAC(nn.Module):
         m = "decoder.model."
 
         def reg(name, t):
-            self.register_buffer(name.replace(".", "_"), t.float().contiguous())
-            return getattr(self, name.replace(".", "_"))
+            # the op lists hold buffer NAMES: nn.Module._apply (.to / .cuda) replaces the buffer objects, so
+            # a tensor reference taken here would stay on the CPU; `_t` resolves the name at call time
+            name = name.replace(".", "_")
+            self.register_buffer(name, t.float().contiguous())
+            return name
 
         def conv(p):
             return reg(p + ".w", _fold_weight_norm(sd, p)), reg(p + ".b", sd[p + ".bias"])
@@ -168,6 +173,7 @@ class DAC(nn.Module):
     def _require_cuda(self):
         if self.device.type != "cuda":
             raise RuntimeError("flowdec_b200.ndac runs on CUDA (sm_100a) only; call .to('cuda')")
+        torch.cuda.set_device(self.device)     # ctypes launches go to the current device
 
     @classmethod
     def load(cls, location, *args, **kwargs):
@@ -178,7 +184,23 @@ class DAC(nn.Module):
         return cls(ckpt["state_dict"], **kw)
 
     # ---------------------------------------------------------------------------------------
+    def _t(self, name):
+        """buffer name (or None) -> the tensor currently registered under it (follows .to() / .cuda())"""
+        return None if name is None else getattr(self, name)
+
+    def op_tensors(self):
+        """every weight / bias / alpha tensor the decoder and encoder op lists refer to, resolved now"""
+        names = []
+        for ops_list in (self._ops, self._enc_ops or []):
+            for op in ops_list:
+                for f in op[1:]:
+                    for g in (f if isinstance(f, tuple) else (f,)):
+                        if isinstance(g, str):
+                            names.append(g)
+        return {n: getattr(self, n) for n in names}
+
     def _conv(self, x, w, b, alpha, dil, pad, res=None, tanh=False):
+        w, b, alpha = self._t(w), self._t(b), self._t(alpha)
         B, Cin, Tin = x.shape
         Cout, _, K = w.shape
         Tout = Tin + 2 * pad - dil * (K - 1)
@@ -195,6 +217,7 @@ class DAC(nn.Module):
                 x = self._conv(x, w, b, a, dil, pad, tanh=tanh)
             elif op[0] == "convtr":
                 _, w, b, a, s, pad = op
+                w, b, a = self._t(w), self._t(b), self._t(a)
                 B, Cin, Tin = x.shape
                 Cout = w.shape[1]
                 Tout = (Tin - 1) * s - 2 * pad + 2 * s
@@ -205,6 +228,7 @@ class DAC(nn.Module):
                 x = out
             elif op[0] == "down":
                 _, w, b, a, s, pad = op
+                w, b, a = self._t(w), self._t(b), self._t(a)
                 B, Cin, Tin = x.shape
                 Cout, _, K = w.shape
                 Tout = (Tin + 2 * pad - K) // s + 1

@@ -55,25 +55,7 @@ def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None, al
     With scale_shift (fp32 [B, Cvirt, 2]) the kernel consumes SiLU(x*scale+shift) instead of x.
     out: NHWC bf16 [.., npad] or fp32 [.., cout]."""
     L = _lib.lib()
-    n = len(srcs)
-    arr = (_lib.ConvSrc * n)()
-    B, H, W = srcs[0][0].shape[:3]
-    for i, src in enumerate(srcs):
-        t, c0, cc, taps = src[:4]
-        assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape[:3] == (B, H, W)
-        arr[i].ptr = t.data_ptr()
-        arr[i].C = t.shape[3]
-        arr[i].c_begin = c0
-        arr[i].c_count = cc
-        arr[i].taps = taps
-        if len(src) > 4 and src[4] is not None:
-            ss, ch_off = src[4], src[5]          # fp32 [B, Cvirt, 2], channel offset of this source in it
-            assert ss.dtype == torch.float32 and ss.is_contiguous() and ss.shape[0] == B
-            arr[i].scale_shift = ss.data_ptr() + ch_off * 8
-            arr[i].ss_pitch = ss.shape[1]
-        else:
-            arr[i].scale_shift = None
-            arr[i].ss_pitch = 0
+    arr, n, B, H, W = _fill_srcs(srcs)
     npad, ktot = wpacked.shape
     out_f32 = out.dtype == torch.float32
     if PROFILE is not None:
@@ -91,6 +73,84 @@ def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None, al
         if algo_k is not None:
             k_algo = algo_k
         PROFILE.append((e0, e1, 2.0 * B * H * W * (algo_cout or out.shape[3]) * k_algo))
+    return out
+
+
+def tensor_conv_ok(B, H, W, npad, seg_channels, out_f32=False):
+    """can fd_conv2d_igemm (tcgen05 tiles) take this conv?  Otherwise conv_direct (CUDA cores) runs it."""
+    if W % 8 or W < 8 or any(c % 64 for c in seg_channels):
+        return False
+    bw = 8
+    while bw < 128 and W % (bw * 2) == 0:
+        bw *= 2
+    if H % (128 // bw):
+        return False
+    return npad in ((16, 48) if out_f32 else (128, 256))
+
+
+def _fill_srcs(srcs):
+    n = len(srcs)
+    arr = (_lib.ConvSrc * n)()
+    B, H, W = srcs[0][0].shape[:3]
+    for i, src in enumerate(srcs):
+        t, c0, cc, taps = src[:4]
+        assert t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape[:3] == (B, H, W)
+        arr[i].ptr = t.data_ptr()
+        arr[i].C = t.shape[3]
+        arr[i].c_begin = c0
+        arr[i].c_count = cc
+        arr[i].taps = taps
+        if len(src) > 4 and src[4] is not None:
+            ss, ch_off = src[4], src[5]          # fp32 [B, Cvirt, 2], channel offset of this source in it
+            assert ss.is_cuda and ss.dtype == torch.float32 and ss.is_contiguous() and ss.shape[0] == B
+            arr[i].scale_shift = ss.data_ptr() + ch_off * 8
+            arr[i].ss_pitch = ss.shape[1]
+        else:
+            arr[i].scale_shift = None
+            arr[i].ss_pitch = 0
+    return arr, n, B, H, W
+
+
+def conv_direct(srcs, wpacked, bias, out, cout=None, affine_only=False):
+    """Shape-generic conv (csrc/fd_generic.cu): same source tuples / packed weights as conv_igemm; any H, W,
+    channel counts multiples of 8.  out: bf16 or fp32 NHWC [B,H,W,pitch >= cout]."""
+    arr, n, B, H, W = _fill_srcs(srcs)
+    rows, ktot = wpacked.shape
+    cout = out.shape[3] if cout is None else cout
+    assert rows >= cout and out.shape[:3] == (B, H, W)
+    rc = _lib.lib().fd_conv2d_direct(arr, n, _lib.ptr(wpacked), ktot, _lib.ptr(bias), _lib.ptr(out),
+                                     int(out.dtype == torch.float32), cout, out.shape[3], B, H, W,
+                                     int(bool(affine_only)), _lib.stream_ptr())
+    _lib.check(rc, "fd_conv2d_direct")
+    return out
+
+
+def attention(qkv, out):
+    """qkv fp32 [B,H,W,3C] (q | k | v), out bf16 [B,H,W,C]: softmax over all H*W positions (AttnBlockpp)"""
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    rc = _lib.lib().fd_attention(_lib.ptr(qkv), B, H * W, C, ctypes.c_float(float(C) ** -0.5), _lib.ptr(out),
+                                 _lib.stream_ptr())
+    _lib.check(rc, "fd_attention")
+    return out
+
+
+def upfirdn2d(x, kernel, up=1, down=1, pad=(0, 0)):
+    """The reference op `upfirdn2d(input, kernel, up, down, pad)` (op/upfirdn2d.py:169-180) on fp32 NCHW CUDA
+    tensors through fd_upfirdn2d_f32; allocates and returns the output like the reference."""
+    up_x = up_y = int(up)
+    down_x = down_y = int(down)
+    px0, px1, py0, py1 = int(pad[0]), int(pad[1]), int(pad[0]), int(pad[1])
+    N, C, H, W = x.shape
+    kh, kw = kernel.shape
+    xc = x.float().contiguous()
+    kc = kernel.to(x.device, torch.float32).contiguous()
+    oh = (H * up_y + py0 + py1 - kh) // down_y + 1
+    ow = (W * up_x + px0 + px1 - kw) // down_x + 1
+    out = torch.empty(N, C, oh, ow, device=x.device, dtype=torch.float32)
+    rc = _lib.lib().fd_upfirdn2d_f32(_lib.ptr(xc), N * C, H, W, _lib.ptr(kc), kh, kw, up_x, up_y, down_x, down_y,
+                                     px0, px1, py0, py1, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "fd_upfirdn2d_f32")
     return out
 
 
@@ -136,6 +196,11 @@ def gn_act_resample(srcs, scale_shift, out, mode, out_raw=None):
     s2 = srcs[1] if len(srcs) > 1 else None
     B, H, W, C1 = s1.shape
     C2 = s2.shape[3] if s2 is not None else 0
+    if mode == 1 and (H % 4 or W % 4):
+        rc = _lib.lib().fd_gn_act_down_any(_lib.ptr(s1), C1, _lib.ptr(s2), C2, _lib.ptr(scale_shift), _lib.ptr(out),
+                                           _lib.ptr(out_raw), B, H, W, _lib.stream_ptr())
+        _lib.check(rc, "fd_gn_act_down_any")
+        return out
     rc = _lib.lib().fd_gn_act_resample(_lib.ptr(s1), C1, _lib.ptr(s2), C2, _lib.ptr(scale_shift),
                                        _lib.ptr(out), _lib.ptr(out_raw), B, H, W, mode, _lib.stream_ptr())
     _lib.check(rc, "fd_gn_act_resample")
@@ -184,6 +249,10 @@ def pyramid_gather(part, bias4, lo, out):
 
 def conv_in(x4, w, b, out):
     B, H, W, _ = x4.shape
+    if out.shape[3] != 64:
+        _lib.check(_lib.lib().fd_conv_in_any(_lib.ptr(x4), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), B, H, W,
+                                             out.shape[3], _lib.stream_ptr()), "fd_conv_in_any")
+        return out
     _lib.check(_lib.lib().fd_conv_in(_lib.ptr(x4), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), B, H, W,
                                      _lib.stream_ptr()), "fd_conv_in")
     return out
@@ -204,6 +273,17 @@ def output_axpy(pyr4, w_out8, base1, c1, base2, c2, coef, out, v_out=None, base3
                                    ctypes.c_float(coef), _lib.ptr(out), _lib.ptr(v_out),
                                    ctypes.c_size_t(npix), _lib.stream_ptr())
     _lib.check(rc, "fd_output_axpy")
+    return out
+
+
+def output_conv3_axpy(pyr4, w72, base1, c1, base2, c2, coef, out, v_out=None, base3=None, c3=0.0):
+    """3x3 output layer (w72: device fp32 [2,4,3,3]) fused with the sampler stage"""
+    B, H, W, _ = pyr4.shape
+    rc = _lib.lib().fd_output_conv3_axpy(_lib.ptr(pyr4), _lib.ptr(w72), _lib.ptr(base1), ctypes.c_float(c1),
+                                         _lib.ptr(base2), ctypes.c_float(c2), _lib.ptr(base3), ctypes.c_float(c3),
+                                         ctypes.c_float(coef), _lib.ptr(out), _lib.ptr(v_out), B, H, W,
+                                         _lib.stream_ptr())
+    _lib.check(rc, "fd_output_conv3_axpy")
     return out
 
 

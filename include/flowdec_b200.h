@@ -179,6 +179,43 @@ int fd_dac_conv_transpose1d(const float* x, const float* w, const float* bias, c
                             float* out, int B, int Cin, int Cout, int Tin, int stride, int pad,
                             fd_stream_t stream);
 
+/* ---- the reference's native op, as a C entry point ------------------------------------------------
+ * upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1) of
+ * flowdec/backbones/ncsnpp_utils/op/upfirdn2d.cpp:38-48 (kernel op/upfirdn2d_kernel.cu:118-218, semantics
+ * op/upfirdn2d.py:182-224): fp32 NCHW input [N,C,in_h,in_w] passed as planes = N*C contiguous images, fp32
+ * kernel [kh,kw]; zero-insertion upsampling, padding (negative = cropping), correlation with the flipped
+ * kernel, decimation.  out fp32 [planes, out_h, out_w] with
+ *   out_h = (in_h*up_y + pad_y0 + pad_y1 - kh) / down_y + 1,  out_w likewise — allocated by the caller
+ * (the reference op allocates it itself, upfirdn2d_kernel.cu:253-254; see INTEGRATION.md §2 for the binding).
+ * The fused backbone path does not call this (it uses fd_gn_act_resample on bf16 NHWC); it is the drop-in for
+ * `upfirdn2d_op.upfirdn2d` so op/upfirdn2d.py:169-180 can bind this library unchanged. */
+int fd_upfirdn2d_f32(const float* input, int planes, int in_h, int in_w, const float* kernel, int kh, int kw,
+                     int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                     float* out, fd_stream_t stream);
+
+/* ---- shape-generic kernels (7-level / bottleneck-attention NCSN++) ------------------
+ * fd_conv2d_direct: same contract and packed weights as fd_conv2d_igemm, for shapes the tcgen05 tiles do not
+ * take: any H, W; segment channel counts multiples of 8; cout rows of wpacked; out bf16 or fp32 NHWC with
+ * channel pitch out_pitch >= cout.  flags bit 0: sources with scale_shift get the affine WITHOUT SiLU
+ * (AttnBlockpp's GroupNorm, layerspp.py:86).  CUDA-core fp32 accumulation of bf16 operands. */
+int fd_conv2d_direct(const struct fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot, const float* bias,
+                     void* out, int out_is_f32, int cout, int out_pitch, int B, int H, int W, int flags,
+                     fd_stream_t stream);
+/* AttnBlockpp core (layerspp.py:91-96): qkv fp32 [B,T,3C] (q | k | v per token, T = H*W) ->
+ * out bf16 [B,T,C] = softmax_j(q_i . k_j * scale) v_j */
+int fd_attention(const float* qkv, int B, int T, int C, float scale, void* out, fd_stream_t stream);
+/* fd_gn_act_resample mode 1 for any even H, W (the tiled / patch kernels need multiples of 4) */
+int fd_gn_act_down_any(const void* src1, int C1, const void* src2, int C2, const float* scale_shift, void* out,
+                       void* out_raw, int B, int H, int W, fd_stream_t stream);
+/* fd_conv_in for cout != 64 (w fp32 OIHW [cout,4,3,3]) */
+int fd_conv_in_any(const void* in4, const float* w, const float* bias, void* out, int B, int H, int W, int cout,
+                   fd_stream_t stream);
+/* fd_output_axpy with a 3x3 output layer (ncsnpp.py:100, output_layer_kwargs.kernel_size = 3):
+ * w72 = DEVICE fp32 [2,4,3,3]; v = Conv3x3(pyr), out = c1*base1 + c2*base2 + c3*base3 + coef*v */
+int fd_output_conv3_axpy(const void* pyr4, const float* w72, const void* base1, float c1, const void* base2,
+                         float c2, const void* base3, float c3, float coef, void* out, void* v_out, int B, int H,
+                         int W, fd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,3 +107,24 @@ def test_dac_encode_oracle_vs_transformers_port():
             assert torch.allclose(lat, lat_ref, rtol=1e-4, atol=1e-5)
             assert torch.allclose(commit, commit_ref.mean(), rtol=1e-4) and torch.allclose(cbl, cb_ref.mean(), rtol=1e-4)
             assert (margin >= 0).all()
+
+
+def test_op_lists_follow_module_to():
+    """nn.Module._apply replaces buffers: the decoder / encoder op lists must resolve tensors at call time
+    (round-1 bug: they kept the construction-time CPU tensors and handed host pointers to the kernels)"""
+    from flowdec_b200.ndac import DAC
+    from flowdec_b200 import _lib
+    sd = D.synth_dac_state_dict(64, 96, (4, 3, 2), 5, seed=1, encoder_dim=8, encoder_rates=(2, 3, 4))
+    m = DAC(sd, decoder_dim=96, decoder_rates=(4, 3, 2), n_codebooks=5, latent_dim=64, sample_rate=48000,
+            encoder_dim=8, encoder_rates=(2, 3, 4))
+    assert m._enc_ops is not None
+    before = m.op_tensors()
+    assert before and all(t.dtype == torch.float32 for t in before.values())
+    m = m.to(torch.float64)
+    after = m.op_tensors()
+    assert set(after) == set(before)
+    for n, t in after.items():
+        assert t.dtype == torch.float64 and t is getattr(m, n), n
+    # and a host tensor can never be turned into a kernel argument
+    with pytest.raises(_lib.FlowDecNativeError):
+        _lib.ptr(torch.zeros(4))

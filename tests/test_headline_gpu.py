@@ -1,0 +1,64 @@
+"""GPU parity of the HEADLINE configuration (BASELINE config 2: midpoint N=3 = NFE 6) against goldens produced by the
+unmodified reference (oracle/make_golden.py --headline -> tests/golden/flowdec_75m_headline.npz): the 0.5 s clip of
+the other goldens and one clip of the config's own length (2 s, Tp = 256, B = 1).
+
+Stated tolerance: waveform SNR >= 30 dB at NFE 6 with bf16 tensor-core operands; the measured
+SNR, SI-SDR and log-spectral MSE (formulas of flowdec/eval/metrics.py) are printed (-s) and recorded in DESIGN.md."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from flowdec_b200.model import build_flowdec
+from flowdec_b200.util.synth import synth_state_dict
+from oracle import metrics as M
+from oracle.make_golden import golden_inputs, headline_inputs
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "flowdec_75m_headline.npz")
+
+
+@pytest.fixture(scope="module")
+def model():
+    m = build_flowdec("75m")
+    m.load_state_dict(synth_state_dict(m.state_dict(), seed=0))
+    return m.cuda()
+
+
+def _report(tag, x, gold):
+    snr, sisdr, lsd = M.snr_db(x, gold), M.si_sdr_db(x, gold), M.logspec_mse(x, gold)
+    print(f"\n{tag}: SNR {snr:.2f} dB, SI-SDR {sisdr:.2f} dB, log-spec MSE {lsd:.4f} dB^2 vs reference golden")
+    return snr, sisdr, lsd
+
+
+def test_headline_midpoint_N3_half_second_clip(model):
+    I = golden_inputs()
+    gold = torch.from_numpy(np.load(GOLD)["enhance_midpoint_N3"])
+    x = model.enhance(I["y"], N=3, solver="midpoint", noise=I["eps"])
+    snr, sisdr, lsd = _report("midpoint N=3 (NFE 6), 0.5 s clip", x, gold)
+    assert x.shape == gold.shape and snr >= 30.0 and sisdr >= 30.0 and lsd <= 0.5
+
+
+def test_headline_midpoint_N3_config2_clip(model):
+    """one clip of BASELINE config 2's shape (2 s -> 251 frames -> Tp 256), alone and inside a batch of 3"""
+    Hh = headline_inputs()
+    gold = torch.from_numpy(np.load(GOLD)["enhance2s_midpoint_N3"])
+    x = model.enhance(Hh["y2"], N=3, solver="midpoint", noise=Hh["eps2"])
+    snr, sisdr, lsd = _report("midpoint N=3 (NFE 6), 2 s clip", x, gold)
+    assert x.shape == gold.shape and snr >= 30.0 and sisdr >= 30.0 and lsd <= 0.5
+    # the same clip as row 1 of a batch (different neighbours): bit-identical (per-sample statistics)
+    g = torch.Generator().manual_seed(1)
+    yb = torch.cat([0.3 * torch.randn(1, 1, 96000, generator=g), Hh["y2"], 0.1 * torch.randn(1, 1, 96000, generator=g)])
+    eb = torch.cat([torch.randn(1, 1, 768, 256, dtype=torch.complex64, generator=g), Hh["eps2"],
+                    torch.randn(1, 1, 768, 256, dtype=torch.complex64, generator=g)])
+    xb = model.enhance(yb, N=3, solver="midpoint", noise=eb)
+    assert torch.equal(xb[1:2], x)
+
+
+def test_heun2_N2_vs_golden(model):
+    I = golden_inputs()
+    gold = torch.from_numpy(np.load(GOLD)["enhance_heun2_N2"])
+    x = model.enhance(I["y"], N=2, solver="heun2", noise=I["eps"])
+    snr, _, _ = _report("heun2 N=2 (NFE 4), 0.5 s clip", x, gold)
+    assert snr >= 30.0

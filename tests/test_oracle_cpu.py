@@ -60,6 +60,20 @@ def test_enhance_vs_golden(sd, gold, N, solver):
     assert rel_l2(x, gold[f"enhance_{solver}_N{N}"]) < 1e-4
 
 
+def test_enhance_headline_nfe6_vs_golden(sd):
+    """the headline solver setting (midpoint N=3 = NFE 6) on the 0.5 s clip: oracle vs the reference's own output
+    (tests/golden/flowdec_75m_headline.npz, oracle/make_golden.py --headline); also ties the metric helpers"""
+    from oracle import metrics as M
+    H = np.load(os.path.join(os.path.dirname(__file__), "golden", "flowdec_75m_headline.npz"))
+    I = golden_inputs()
+    with torch.no_grad():
+        x = O.enhance(sd, I["y"], N=3, solver="midpoint", eps=I["eps"])
+    g = torch.from_numpy(H["enhance_midpoint_N3"])
+    assert rel_l2(x, g) < 1e-3
+    assert M.snr_db(x, g) > 60 and M.si_sdr_db(x, g) > 60 and M.logspec_mse(x, g) < 1e-3
+    assert abs(M.snr_db(0.9 * g, g) - 20.0) < 1e-4 and M.si_sdr_db(0.9 * g, g) > 100
+
+
 def test_scoredec_pc_sampler_vs_golden(sd, gold):
     I = golden_inputs()
     with torch.no_grad():

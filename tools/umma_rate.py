@@ -3,9 +3,9 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes
 import torch
-from flowdec_b200 import _lib
+from tools import probe_lib
 
-L = _lib.lib()
+L = probe_lib.load()
 L.fd_umma_rate.restype = ctypes.c_int
 L.fd_umma_rate.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p]
 A = torch.randn(256, 64, device="cuda").to(torch.bfloat16)
