@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--variant", default="75m")
     ap.add_argument("--max-batch", type=int, default=0, help="clips per backbone pass (0 = model default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config3 / config4 / shard-check records")
     ap.add_argument("--streams", type=int, default=0, help="micro-batches in flight (0 = model default)")
     return ap.parse_args()
 
@@ -138,16 +139,19 @@ def pick_cpu_threads():
 _CPU_STATE = {}
 
 
-def cpu_port_time(threads, seconds_clip=0.5, N=1, solver="euler"):
-    """Times the CPU oracle (port of the reference algorithm) on a bounded sample: one clip of
-    `seconds_clip` with one Euler step (NFE 1).  Cost is linear in B*Tp*NFE (conv dominated,
-    BASELINE.md §4), so the workload's time = sec_per_(frame*NFE) * Tp * NFE * batch."""
+def cpu_port_time(threads, seconds_clip=2.0, N=3, solver="midpoint"):
+    """Times the CPU oracle (port of the reference algorithm) DIRECTLY on one clip of the workload's own length
+    and solver setting: 1 clip x `seconds_clip` at (N, solver).  The reference processes clips
+    independently and its cost is linear in the batch, so audio-s/s of the whole batch = seconds_clip / time."""
     from flowdec_b200.model import build_flowdec
     from flowdec_b200.util.synth import synth_state_dict, synth_waveforms
     from oracle import flowdec_oracle as O
     torch.set_num_threads(threads)
     if "sd" not in _CPU_STATE:
         _CPU_STATE["sd"] = synth_state_dict(build_flowdec("75m").state_dict(), seed=0)
+        with torch.no_grad():      # page in MKL-DNN / the thread pool outside the timed sample
+            O.enhance(_CPU_STATE["sd"], synth_waveforms(1, 12000, seed=1), N=1, solver="euler",
+                      eps=torch.zeros(1, 1, 768, 64, dtype=torch.complex64))
     sd = _CPU_STATE["sd"]
     L = int(seconds_clip * SR)
     y = synth_waveforms(1, L, seed=1234)
@@ -158,32 +162,26 @@ def cpu_port_time(threads, seconds_clip=0.5, N=1, solver="euler"):
         O.enhance(sd, y, N=N, solver=solver, eps=eps)
     dt = time.perf_counter() - t0
     nfe = nfe_of(N, solver)
-    frames_sample = padded_frames(L)
-    sec_per_frame_nfe = dt / (frames_sample * nfe)
-    return dt, sec_per_frame_nfe, (f"oracle port, 1 clip x {seconds_clip} s ({frames_sample} frames), {solver} N={N} "
-                                   f"(NFE {nfe}), {dt:.1f} s on {threads} threads; scaled linearly in frames x NFE")
+    return dt, (f"oracle port, 1 clip x {seconds_clip:g} s ({padded_frames(L)} frames), {solver} N={N} (NFE {nfe}) timed "
+                f"directly: {dt:.1f} s on {threads} threads; batch scaled linearly (clips are independent)")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = pick_cpu_threads()
-    L = int(args.seconds * SR)
-    Tp = padded_frames(L)
-    nfe = nfe_of(args.N, args.solver)
-    times = []
-    sample = ""
+    times, sample = [], ""
     t_start = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        dt, spf, sample = cpu_port_time(threads)
-        if i >= args.warmup or (time.perf_counter() - t_start) > 100:
-            times.append(spf)
+        dt, sample = cpu_port_time(threads, args.seconds, args.N, args.solver)
+        # every pass is the same deterministic CPU work: under the time budget warm-up passes count as samples
+        if i >= args.warmup or (time.perf_counter() - t_start) > 60:
+            times.append(dt)
         if (time.perf_counter() - t_start) > 150:      # keep the whole run within a few minutes
             break
-    spf = sum(times) / len(times)
-    # one step of the workload = batch clips of `seconds`, NFE evaluations of Tp frames each
-    t_step = spf * Tp * nfe * args.batch * args.gpus
-    value = args.batch * args.gpus * args.seconds / t_step
+    dt = sum(times) / len(times)
+    t_step = dt * args.batch * args.gpus               # one step = the whole batch, clip after clip
+    value = args.seconds / dt
     line = {
         "impl": "reference", "metric": "48kHz audio-seconds/sec (RTF^-1) flowdec_75m NFE=6", "value": value,
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
@@ -204,6 +202,42 @@ def workload_config(args):
             "solver": args.solver, "sharding": f"dp{args.gpus} (clip batch, no data-path collective)",
             "l2": "working set (multi-GB activations per micro-batch) >> 126 MB L2; no explicit flush",
             "micro_batch": "16 clips (<= 4096 padded frames) per backbone pass, 2 passes in flight on separate CUDA streams (model.max_batch / overlap_streams)"}
+
+
+def ndac_pipeline_record(model, args, dev, steps=3):
+    """codes -> quantizer.from_codes -> DAC.decode -> FlowModel.enhance (demo.ipynb:104-109) on one GPU, with the
+    share of each stage (CUDA events).  Synthetic NDAC-75-scale decoder: latent 1024, decoder_dim 1536, rates
+    8*5*4*4 = 640 (75 Hz frames at 48 kHz), 10 codebooks; exact dims live in the (offline-unavailable) checkpoint."""
+    from flowdec_b200.ndac import DAC
+    from flowdec_b200.util.synth import synth_dac_state_dict
+    rates, nq, latent, dim = (8, 5, 4, 4), 10, 1024, 1536
+    dac = DAC(synth_dac_state_dict(latent, dim, rates, nq, seed=7), decoder_dim=dim, decoder_rates=rates,
+              n_codebooks=nq, latent_dim=latent, sample_rate=SR).to(dev).eval()
+    B = args.batch
+    Tz = int(args.seconds * SR) // 640
+    codes = torch.randint(0, 1024, (B, nq, Tz), generator=torch.Generator().manual_seed(3)).to(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    tot = [0.0, 0.0, 0.0]
+    for it in range(steps + 2):
+        ev[0].record()
+        zq, _, _ = dac.quantizer.from_codes(codes)
+        ev[1].record()
+        xh = dac.decode(zq)
+        ev[2].record()
+        out = model.enhance(xh, N=args.N, solver=args.solver)
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            for i in range(3):
+                tot[i] += ev[i].elapsed_time(ev[i + 1])
+    assert torch.isfinite(out).all()
+    ms = [t / steps for t in tot]
+    model.reset_cache()
+    return {"workload": f"{B} x {args.seconds:g} s: codes [B,{nq},{Tz}] -> from_codes -> decode (dim {dim}, rates {rates}) "
+                        f"-> enhance NFE {nfe_of(args.N, args.solver)}; synthetic weights",
+            "value": B * args.seconds / (sum(ms) * 1e-3), "unit": "audio-s/s", "from_codes_ms": ms[0],
+            "decode_ms": ms[1], "enhance_ms": ms[2], "decode_share": ms[1] / sum(ms),
+            "decode_audio_s_per_s": B * args.seconds / (ms[1] * 1e-3)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -329,7 +363,8 @@ def main():
         if os.path.exists(tp):
             tj = json.load(open(tp))
             traffic = tj["dram_bytes_per_launch"]
-            traffic_note = (f"ncu dram read+write of the dominant launch shape ({tj['launch_shape']}); algorithmic "
+            traffic_note = (f"STATIC ncu capture ({tj.get('source', 'profiles/')}), not measured in this run: "
+                            f"dram read+write of the dominant launch shape ({tj['launch_shape']}); algorithmic "
                             f"{tj['algorithmic_bytes_per_launch']} B; tensor pipe active {tj['tensor_pipe_active_pct_of_elapsed']} % of elapsed")
         roofline = {"bound": "tensor", "kernel": "conv_halo_kernel / conv_igemm_kernel (tcgen05 implicit GEMM, GroupNorm+SiLU operand transform fused)", "achieved": achieved,
                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
@@ -340,12 +375,58 @@ def main():
                     "whole_step_tflops": algo_flops_step / (ms / args.steps * 1e-3) / 1e12,
                     "whole_step_frac": algo_flops_step / (ms / args.steps * 1e-3) / 1e12 / peak}
 
+    # ---- secondary records (outside the headline timed region; own keys) ----
+    def timed_config(m, batch, seconds, steps=2):
+        """same timing protocol (device-resident inputs, CUDA events, max over ranks) for another BASELINE config"""
+        Lc = int(seconds * SR)
+        yc = synth_waveforms(batch, Lc, seed=5000 + rank * batch).to(dev)
+        for _ in range(3):
+            m.enhance(yc, N=args.N, solver=args.solver)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            m.enhance(yc, N=args.N, solver=args.solver)
+        b.record()
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms = float(tt[0])
+        m.reset_cache()
+        return {"value": batch * world * seconds * steps / (t_ms * 1e-3), "unit": "audio-s/s",
+                "ms_per_step": t_ms / steps, "steps": steps, "per_gpu_batch": batch, "clip_seconds": seconds}
+
+    extras = {}
+    if not args.no_extras:
+        model.reset_cache()
+        # BASELINE config 4: 256 x 4 s over 8 GPUs = 32 x 4 s per GPU (here: this many GPUs' worth of it)
+        extras["config4"] = dict(timed_config(model, 32, 4.0),
+                                 workload=f"flowdec_75m, {32 * world} x 4 s clips, NFE {nfe}, 32 per GPU on {world} GPU(s)")
+        if world == 1:
+            # BASELINE config 3: flowdec_25s (same backbone, its own sigma_y curve), 64 x 2 s
+            m25 = build_flowdec("25s")
+            m25.backbone, m25.feature_extractor = model.backbone, model.feature_extractor
+            m25 = m25.to(dev)
+            extras["config3"] = dict(timed_config(m25, 64, 2.0), workload=f"flowdec_25s, 64 x 2 s clips, NFE {nfe}, 1 GPU")
+            del m25
+        if world == 1:
+            extras["ndac_pipeline"] = ndac_pipeline_record(model, args, dev)
+        if dist is not None:
+            from flowdec_b200 import parallel
+            ok = parallel.verify_sharding(model, dist, L, args.N, args.solver)
+            extras["shard_bitwise_equal"] = ok
+            extras["shard_check"] = (f"{2 * world} clips x {args.seconds:g} s: NCCL scatter from rank 0 -> enhance per rank "
+                                     f"(noise seeded by global clip index) -> NCCL all_gather, compared bit for bit "
+                                     f"with the same batch enhanced on rank 0 alone")
+            model.reset_cache()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = pick_cpu_threads()
-        dt, spf, sample = cpu_port_time(threads)
-        v = args.seconds / (spf * Tp * nfe)
-        cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample}
+        dt, sample = cpu_port_time(threads, args.seconds, args.N, args.solver)
+        cpu_baseline = {"value": args.seconds / dt, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                        "sample": sample}
 
     if rank == 0:
         line = {
@@ -359,6 +440,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+        line.update(extras)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

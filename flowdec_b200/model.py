@@ -112,19 +112,19 @@ class FlowModel(EnhancementModel):
         self._streams = []
         self._sig_cache = None
 
-    def _drop_graphs(self):
+    def reset_cache(self):
         self._graphs = OrderedDict()
         self._sig_cache = None
         if hasattr(self.backbone, "pin_workspaces"):
             self.backbone.pin_workspaces(set())
 
     def _apply(self, fn, *a, **k):
-        self._drop_graphs()
+        self.reset_cache()
         self._streams = []
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict=None, **kw):
-        self._drop_graphs()
+        self.reset_cache()
         return super().load_state_dict(state_dict, strict=self.strict_loading if strict is None else strict, **kw)
 
     # ------------------------------------------------------------------------------------
@@ -215,7 +215,8 @@ class FlowModel(EnhancementModel):
                     tmp=torch.empty(B, 768, Tp, 2, **f32), out=torch.empty(B, L, **f32))
 
     def _entry(self, B, Tp, N, solver, sigma_fac, dev):
-        key = (B, Tp, int(N), solver, float(sigma_fac))
+        # the micro-batch split and the lane count are baked into a captured graph
+        key = (B, Tp, int(N), solver, float(sigma_fac), self._micro_batch(Tp), int(self.overlap_streams))
         entry = self._graphs.get(key)
         if entry is None:
             while len(self._graphs) >= max(1, self.graph_cache_size):

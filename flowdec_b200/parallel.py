@@ -40,3 +40,45 @@ def enhance_sharded(model_fn, y, N, solver, rank, world, seed=4321, gather=None)
     if gather is None:
         return out, (lo, hi)
     return gather(out, [shard_bounds(B, world, r) for r in range(world)])
+
+
+def nccl_scatter_enhance_gather(model, dist, y_full, N, solver, seed=4321):
+    """The sharded form of enhance() with its two collectives on the wire: rank 0 holds the full
+    batch y_full [B,1,L] on its GPU; `dist.scatter` hands every rank its contiguous shard (NCCL over NVLink),
+    each rank enhances it with noise seeded by GLOBAL clip index, `dist.all_gather_into_tensor` returns the full
+    enhanced batch to every rank.  B must be divisible by the world size (equal shards, as NCCL scatter needs);
+    y_full is only read on rank 0 (other ranks may pass an empty tensor of the same shape/dtype on their device)."""
+    from .util.other import padded_frames
+    world, rank = dist.get_world_size(), dist.get_rank()
+    B, _, L = y_full.shape
+    if B % world:
+        raise ValueError(f"batch {B} is not divisible by the world size {world}")
+    per = B // world
+    dev = y_full.device
+    shard = torch.empty(per, 1, L, device=dev, dtype=torch.float32)
+    dist.scatter(shard, [c.contiguous() for c in y_full.split(per)] if rank == 0 else None, src=0)
+    Tp = padded_frames(1 + L // 384)
+    noise = torch.stack([clip_noise(i, Tp, seed) for i in range(rank * per, (rank + 1) * per)], 0).to(dev)
+    out = model.enhance(shard, N=N, solver=solver, noise=noise).contiguous()
+    full = torch.empty(B, 1, L, device=dev, dtype=torch.float32)
+    dist.all_gather_into_tensor(full, out)
+    return full
+
+
+def verify_sharding(model, dist, L, N, solver, clips_per_rank=2, seed=4321, wave_seed=777):
+    """Hardware check of the sharding contract: the batch enhanced in shards on all ranks (scatter -> enhance ->
+    all_gather) must equal, BIT FOR BIT, the same batch enhanced on rank 0 alone.  Returns True/False on rank 0
+    (None elsewhere)."""
+    from .util.other import padded_frames
+    from .util.synth import synth_waveforms
+    world, rank = dist.get_world_size(), dist.get_rank()
+    B = clips_per_rank * world
+    dev = model.device
+    y = synth_waveforms(B, L, seed=wave_seed).to(dev) if rank == 0 else torch.empty(B, 1, L, device=dev)
+    full = nccl_scatter_enhance_gather(model, dist, y, N, solver, seed)
+    if rank != 0:
+        return None
+    Tp = padded_frames(1 + L // 384)
+    noise = torch.stack([clip_noise(i, Tp, seed) for i in range(B)], 0).to(dev)
+    alone = model.enhance(y, N=N, solver=solver, noise=noise)
+    return bool(torch.equal(alone, full))

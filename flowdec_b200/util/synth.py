@@ -80,3 +80,65 @@ def synth_waveforms(batch, length, seed=1234, kind="tones", sr=48000):
         x = 0.5 * x / x.abs().max()
         out[i, 0] = x.float()
     return out
+
+
+def synth_dac_state_dict(latent_dim, decoder_dim, rates, n_codebooks, codebook_size=1024, codebook_dim=8,
+                         seed=0, encoder_dim=None, encoder_rates=None):
+    """descript-style decoder + quantizer state_dict with seeded non-degenerate values"""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(p, cout, cin, k, transpose=False):
+        shape = (cin, cout, k) if transpose else (cout, cin, k)
+        v = torch.randn(shape, generator=g)
+        fan = cin * k if not transpose else cin * k / 2
+        sd[p + ".weight_v"] = v
+        sd[p + ".weight_g"] = (torch.rand(shape[0], 1, 1, generator=g) + 0.5) * (
+            v.norm(dim=(1, 2), keepdim=True) / math.sqrt(fan) * (math.sqrt(cin / cout) if transpose else 1.0))
+        sd[p + ".bias"] = 0.05 * torch.randn(cout, generator=g)
+
+    def alpha(p, c):
+        sd[p] = 0.5 + torch.rand(1, c, 1, generator=g)
+
+    for i in range(n_codebooks):
+        q = f"quantizer.quantizers.{i}."
+        sd[q + "codebook.weight"] = torch.randn(codebook_size, codebook_dim, generator=g)
+        conv(q + "out_proj", latent_dim, codebook_dim, 1)
+        conv(q + "in_proj", codebook_dim, latent_dim, 1)
+    m = "decoder.model."
+    conv(m + "0", decoder_dim, latent_dim, 7)
+    ch = decoder_dim
+    for i, s in enumerate(rates):
+        b = f"{m}{i + 1}.block."
+        alpha(b + "0.alpha", ch)
+        conv(b + "1", ch // 2, ch, 2 * s, transpose=True)
+        ch //= 2
+        for j in range(3):
+            r = f"{b}{j + 2}.block."
+            alpha(r + "0.alpha", ch)
+            conv(r + "1", ch, ch, 7)
+            alpha(r + "2.alpha", ch)
+            conv(r + "3", ch, ch, 1)
+    n = len(rates)
+    alpha(f"{m}{n + 1}.alpha", ch)
+    conv(f"{m}{n + 2}", 1, ch, 7)
+    if encoder_dim is not None:          # drawn last so the decoder / quantizer values above do not change
+        e = "encoder.block."
+        conv(e + "0", encoder_dim, 1, 7)
+        ch = encoder_dim
+        for i, st in enumerate(encoder_rates):
+            b = f"{e}{i + 1}.block."
+            for j in range(3):
+                r = f"{b}{j}.block."
+                alpha(r + "0.alpha", ch)
+                conv(r + "1", ch, ch, 7)
+                alpha(r + "2.alpha", ch)
+                conv(r + "3", ch, ch, 1)
+            alpha(b + "3.alpha", ch)
+            conv(b + "4", 2 * ch, ch, 2 * st)
+            ch *= 2
+        n = len(encoder_rates)
+        alpha(f"{e}{n + 1}.alpha", ch)
+        conv(f"{e}{n + 2}", latent_dim, ch, 3)
+        sd[f"{e}{n + 2}.weight_g"] *= 0.05        # residual stacks grow the activations; keep z = O(1)
+    return sd

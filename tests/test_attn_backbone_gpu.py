@@ -45,7 +45,7 @@ def test_conv_direct(B, H, W, segs, cout, taps, f32):
     out = torch.empty(B, H, W, cout, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
     ops.conv_direct([(s, 0, s.shape[3], taps) for s in srcs], wp, bias.cuda(), out)
     xr = torch.cat([s.float().cpu().permute(0, 3, 1, 2) for s in srcs], 1)
-    ref = F.conv2d(xr, w.to(torch.bfloat16).float(), bias, padding=taps // 3)
+    ref = F.conv2d(xr, w.to(torch.bfloat16).float(), bias, padding=1 if taps == 9 else 0)
     got = out.float().cpu().permute(0, 3, 1, 2)
     assert rel_l2(got, ref) < (1e-5 if f32 else 4e-3)
 

@@ -125,7 +125,7 @@ def test_batch_independence_and_microbatching(model):
     eps = torch.randn(3, 1, 768, 64, dtype=torch.complex64, generator=g)
     full = model.enhance(y, N=1, solver="midpoint", noise=eps)
     model.max_batch = 2
-    model._graphs = {}
+    model.reset_cache()         # micro-batch size is baked into the cached graphs
     split = model.enhance(y, N=1, solver="midpoint", noise=eps)
     model.max_batch = 16
     one = model.enhance(y[1:2], N=1, solver="midpoint", noise=eps[1:2])

@@ -67,3 +67,37 @@ def test_shard_bounds_cover():
             assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
     a = parallel.clip_noise(7, 64)
     assert torch.equal(a, parallel.clip_noise(7, 64)) and not torch.equal(a, parallel.clip_noise(8, 64))
+
+
+class _FakeModel:
+    """stands in for FlowModel on CPU: per-clip, batch-composition independent, consumes the injected noise"""
+    device = torch.device("cpu")
+
+    def enhance(self, y, N, solver, noise):
+        return y * 0.25 + noise.real.mean(dim=(-2, -1)).reshape(-1, 1, 1) * N
+
+
+def _worker_verify(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = parallel.verify_sharding(_FakeModel(), dist, 1536, 3, "midpoint", clips_per_rank=3)
+    if rank == 0:
+        ret.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_scatter_enhance_gather_world2():
+    """the collective form bench.py runs on hardware at N > 1 (scatter from rank 0 -> per-rank enhance with
+    global-index noise -> all_gather -> bitwise comparison with the unsharded run), here over gloo"""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker_verify, args=(r, 2, 29613, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok is True

@@ -37,7 +37,7 @@ def main():
         for name, lib in (("default", ""), ("variant", VARIANT)):
             env = dict(os.environ, FD_LIB_PATH=lib)
             r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3",
-                                "--no-cpu-baseline"] + args, env=env, capture_output=True, text=True, timeout=900)
+                                "--no-cpu-baseline", "--no-extras"] + args, env=env, capture_output=True, text=True, timeout=900)
             try:
                 d = json.loads(r.stdout.strip().splitlines()[-1])
                 print(f"{name:8s} {d['value']:8.2f} audio-s/s  e2e {d['e2e']['value']:8.2f}  clk {d['clocks']['sm_mhz']:6.0f} MHz  "

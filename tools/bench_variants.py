@@ -15,7 +15,7 @@ def patched(self, *a, **k):
 
 
 N.NCSNpp.__init__ = patched
-sys.argv = ["bench.py", "--steps", "3", "--warmup", "3", "--no-cpu-baseline"] + sys.argv[1:]
+sys.argv = ["bench.py", "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-extras"] + sys.argv[1:]
 buf = io.StringIO()
 with contextlib.redirect_stdout(buf):
     runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"), run_name="__main__")

@@ -22,7 +22,7 @@ def main(tag):
     out = os.path.join(ROOT, "profiles", f"{tag}_configs.jsonl")
     with open(out, "w") as f:
         for name, extra in RUNS:
-            cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--no-cpu-baseline"] + extra
+            cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--no-extras"] + extra
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
             try:
