@@ -67,6 +67,10 @@ SIGNATURES = {
     "fd_dac_conv1d_strided": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "fd_rvq_encode": [_P] * 13 + [_I] * 6 + [_P],
     "fd_fir_tiles_enable": [_I],
+    "fd_chan_stats_f32": [_P, _I, _I, _I, _P, _I, _P],
+    "fd_gn_act_resample_f32": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P],
+    "fd_conv_in_f32": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "fd_combine_f32": [_P, _P, _P, _P, _P, _Z, _I, _P],
     "fd_upfirdn2d_f32": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "fd_conv2d_direct": [ctypes.POINTER(ConvSrc), _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "fd_attention": [_P, _I, _I, _I, _F, _P, _P],

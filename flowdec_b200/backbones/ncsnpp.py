@@ -220,8 +220,30 @@ class NCSNpp(nn.Module):
         self.stats_slabs = 64
         self.fuse_stats = True     # GroupNorm partial sums produced by the conv epilogue
         self.pyramid_shift_after_gemm = True
+        self.pyramid_halo = True        # pyramid convs on the N = 16 halo kernel with the fused transform
         self.fuse_gn_into_conv = True   # GroupNorm+SiLU applied inside the conv kernel (needs ops.HALO_TILES)
         self.max_ctas = 0
+        self.precision = "bf16"
+
+    def set_precision(self, precision):
+        """"bf16" (default): bf16 operands / activation storage, fp32 accumulation.  "tf32": fp32 activation
+        storage, tf32 tensor-core operands (kind::tf32) — the precision class of the reference's own GPU convs
+        (cuDNN with allow_tf32, layers.py:110-134); about half the conv throughput and twice the activation bytes.
+        The tf32 kernels exist for shapes the halo tiles take (the FlowDec configuration family)."""
+        if precision not in ("bf16", "tf32"):
+            raise ValueError(f"precision must be 'bf16' or 'tf32', got {precision!r}")
+        if precision != self.precision:
+            self.precision = precision
+            self._invalidate()
+            self._workspaces = OrderedDict()
+        return self
+
+    @property
+    def _adt(self):
+        return torch.float32 if self.precision == "tf32" else torch.bfloat16
+
+    def _pack(self, segs, rows):
+        return ops.pack_conv_weight(segs, rows, tf32=self.precision == "tf32")
 
     # ------------------------------------------------------------------ parameter management
     def _invalidate(self):
@@ -329,7 +351,7 @@ class NCSNpp(nn.Module):
                 if isinstance(m, ResnetBlockBigGANpp):
                     e = {}
                     cin, cout = m.in_ch, m.out_ch
-                    e["w0"] = ops.pack_conv_weight([(m.Conv_0.weight.float(), 9)], self._npad(cout))
+                    e["w0"] = self._pack([(m.Conv_0.weight.float(), 9)], self._npad(cout))
                     e["w0_full"] = m.Conv_0.weight.float()
                     e["b0"] = m.Conv_0.bias.float().contiguous()
                     w1 = m.Conv_1.weight.float() * inv
@@ -370,7 +392,7 @@ class NCSNpp(nn.Module):
                 elif isinstance(m, nn.Conv2d) and i > 3:     # pyramid conv C -> 4
                     b16 = torch.zeros(16, device=dev)
                     b16[:m.bias.shape[0]] = m.bias.float()
-                    P[i] = dict(w=ops.pack_conv_weight([(m.weight.float(), 9)], 16), b=b16,
+                    P[i] = dict(w=self._pack([(m.weight.float(), 9)], 16), b=b16,
                                 wt=ops.pack_tap_weight(m.weight.float()), b4=m.bias.float().contiguous())
             P["conv_in_w"] = self.all_modules[3].weight.float().contiguous()
             P["conv_in_b"] = self.all_modules[3].bias.float().contiguous()
@@ -396,7 +418,7 @@ class NCSNpp(nn.Module):
                 segs.append((e["w2_full"][:, c0:c0 + c].contiguous(), 1))
                 c0 += c
             assert c0 == e["w2_full"].shape[1]
-            wp = ops.pack_conv_weight(segs, self._npad(cout))
+            wp = self._pack(segs, self._npad(cout))
             e["w1_cache"][key] = wp
         return wp
 
@@ -411,7 +433,7 @@ class NCSNpp(nn.Module):
             for c in seg_channels:
                 segs.append((e["w0_full"][:, c0:c0 + c].contiguous(), 9))
                 c0 += c
-            wp = ops.pack_conv_weight(segs, self._npad(cout))
+            wp = self._pack(segs, self._npad(cout))
             e["w1_cache"][key] = wp
         return wp
 
@@ -471,8 +493,8 @@ class NCSNpp(nn.Module):
         C = sum(s.shape[3] for s in srcs)
         ss = self._gn_scale_shift(srcs, gamma, beta, scache, "gn_ss")
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
-        a = self._ws.get(name, (B, Ho, Wo, C), torch.bfloat16, srcs[0].device)
-        raw = self._ws.get(raw_name, (B, Ho, Wo, C), torch.bfloat16, srcs[0].device) if raw_name else None
+        a = self._ws.get(name, (B, Ho, Wo, C), self._adt, srcs[0].device)
+        raw = self._ws.get(raw_name, (B, Ho, Wo, C), self._adt, srcs[0].device) if raw_name else None
         ops.gn_act_resample(srcs, ss, a, mode, out_raw=raw)
         return (a, raw) if raw_name else a
 
@@ -484,6 +506,8 @@ class NCSNpp(nn.Module):
         B, H, W, cout = out.shape
         if scache is not None:
             scache.pop(out.data_ptr(), None)
+        if self.precision == "tf32" and not ops.halo_eligible(B, H, W, wp.shape[0]):
+            raise NotImplementedError(f"tf32 precision: conv at {B}x{H}x{W} -> {cout} does not fit the halo tiles")
         if ops.tensor_conv_ok(B, H, W, wp.shape[0], [s[2] for s in srcs]) and \
                 (all(len(s) <= 4 or s[4] is None for s in srcs) or ops.halo_eligible(B, H, W, wp.shape[0])):
             st = None
@@ -528,7 +552,7 @@ class NCSNpp(nn.Module):
         else:
             a0 = self._gn_act(srcs, e["g0"], e["be0"], mode, scache, "act")
             conv0_srcs, w0 = [(a0, 0, cin, 9)], e["w0"]
-        h1 = self._ws.get("h1", (B, Ho, Wo, cout), torch.bfloat16, dev)
+        h1 = self._ws.get("h1", (B, Ho, Wo, cout), self._adt, dev)
         self._conv(conv0_srcs, w0, tb[i], h1, stats_name="h1_stats_c", scache=scache)
         if halo or not tensor1:
             ss1 = self._gn_scale_shift([h1], e["g1"], e["be1"], scache, "gn_ss1")
@@ -538,7 +562,7 @@ class NCSNpp(nn.Module):
         scache.pop(h1.data_ptr(), None)
         skip = [xr] if mode != 0 else list(srcs)
         wp = self._skip_weight(e, [s.shape[3] for s in skip], cout)
-        out = self._ws.get(f"rb{i}", (B, Ho, Wo, cout), torch.bfloat16, dev)
+        out = self._ws.get(f"rb{i}", (B, Ho, Wo, cout), self._adt, dev)
         algo_k = 9 * cout + (cin if hasattr(m, "Conv_2") else 0)
         self._conv([conv1_main] + [(s, 0, s.shape[3], 1) for s in skip], wp, e["b1"], out,
                    stats_name=f"rb{i}_stats_c" if want_stats else None, algo_k=algo_k, scache=scache)
@@ -552,8 +576,8 @@ class NCSNpp(nn.Module):
         ss = self._gn_scale_shift([h], e["g"], e["be"], scache, "attn_ss")
         qkv = self._ws.get("attn_qkv", (B, H, W, 3 * C), torch.float32, h.device)
         ops.conv_direct([(h, 0, C, 1, ss, 0)], e["wqkv"], e["bqkv"], qkv, affine_only=True)
-        a = ops.attention(qkv, self._ws.get("attn_a", (B, H, W, C), torch.bfloat16, h.device))
-        out = self._ws.get(f"attn{i}", (B, H, W, C), torch.bfloat16, h.device)
+        a = ops.attention(qkv, self._ws.get("attn_a", (B, H, W, C), self._adt, h.device))
+        out = self._ws.get(f"attn{i}", (B, H, W, C), self._adt, h.device)
         scache.pop(out.data_ptr(), None)
         return ops.conv_direct([(a, 0, C, 1), (h, 0, C, 1)], e["wo"], e["bo"], out)
 
@@ -583,7 +607,7 @@ class NCSNpp(nn.Module):
         self._stat_counter = 0
         mods = self.all_modules
         pyr_in = ops.pack4(x, y, ws.get("pyr_in0", (B, Fq, T, 4), torch.float32, dev))
-        h = ops.conv_in(pyr_in, P["conv_in_w"], P["conv_in_b"], ws.get("h_in", (B, Fq, T, self.nf), torch.bfloat16, dev))
+        h = ops.conv_in(pyr_in, P["conv_in_w"], P["conv_in_b"], ws.get("h_in", (B, Fq, T, self.nf), self._adt, dev))
         hs = [h]
         idx = 4
         H, W = Fq, T
@@ -597,7 +621,7 @@ class NCSNpp(nn.Module):
                 H, W = H // 2, W // 2
                 pyr_in = ops.fir_down4(pyr_in, ws.get(f"pyr_in{lvl + 1}", (B, H, W, 4), torch.float32, dev))
                 c = P[idx]
-                hc = ops.combine(pyr_in, c["w"], c["b"], hd, ws.get(f"comb{idx}", hd.shape, torch.bfloat16, dev))
+                hc = ops.combine(pyr_in, c["w"], c["b"], hd, ws.get(f"comb{idx}", hd.shape, self._adt, dev))
                 scache.pop(hc.data_ptr(), None)
                 idx += 1
                 hs.append(hc)
@@ -619,7 +643,13 @@ class NCSNpp(nn.Module):
             pc = P[idx]
             C = h.shape[3]
             ph = ws.get(f"pyr_out{lvl}", (B, H, W, 4), torch.float32, dev)
-            if self.pyramid_shift_after_gemm and ops.tensor_conv_ok(B, H, W, 48, [C], out_f32=True):
+            if self.pyramid_halo and ops.halo_eligible(B, H, W, 16) and C % 64 == 0:
+                # 3x3 conv C -> 4 on the halo kernel (N = 16): GroupNorm+SiLU in the operand transform, one read of
+                # h, fp32 float4 per pixel out; nothing is materialised
+                ss = self._gn_scale_shift([h], g["g"], g["b"], scache, "gn_ss")
+                ops.conv_igemm([(h, 0, C, 9, ss, 0)], pc["w"], pc["b"], ph, self.max_ctas)
+                pyramid = ph if pyramid is None else ops.pyramid_up_add(pyramid, ph, ph)
+            elif self.pyramid_shift_after_gemm and ops.tensor_conv_ok(B, H, W, 48, [C], out_f32=True):
                 # one pass over `a`: 36 per-tap products per pixel on tensor cores, then a gather-sum
                 a = self._gn_act([h], g["g"], g["b"], 0, scache, "act")
                 part = ws.get("pyr_part", (B, H, W, 36), torch.float32, dev)

@@ -145,6 +145,48 @@ __device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], uint32_t 
   }
 }
 
+// fp32-output form (tf32 kernels): one 32-column chunk = one 128-byte staging row of 32 floats.
+__device__ __forceinline__ void epilogue_chunk_f32(const uint32_t (&v)[32], uint32_t bs_addr, uint32_t rowp_addr,
+                                                   int row, float* stat_dst, int lane, uint32_t scratch) {
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b4 = lds_f4(bs_addr + i * 16);
+    const float2 lo = fadd2(make_float2(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1])),
+                            make_float2(b4.x, b4.y));
+    const float2 hi = fadd2(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])),
+                            make_float2(b4.z, b4.w));
+    f[4 * i + 0] = lo.x; f[4 * i + 1] = lo.y; f[4 * i + 2] = hi.x; f[4 * i + 3] = hi.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 q;
+    q.x = __float_as_uint(f[4 * j + 0]);
+    q.y = __float_as_uint(f[4 * j + 1]);
+    q.z = __float_as_uint(f[4 * j + 2]);
+    q.w = __float_as_uint(f[4 * j + 3]);
+    sts128(rowp_addr + static_cast<uint32_t>((j ^ (row & 7)) << 4), q);
+  }
+  if (stat_dst != nullptr) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(scratch + static_cast<uint32_t>(lane * 144 + i * 16)),
+                   "f"(f[4 * i]), "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3]) : "memory");
+    __syncwarp();
+    float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 32; r += 2) {
+      float2 ab;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ab.x) : "r"(scratch + static_cast<uint32_t>(r * 144 + lane * 4)));
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ab.y) : "r"(scratch + static_cast<uint32_t>((r + 1) * 144 + lane * 4)));
+      s2 = fadd2(s2, ab);
+      q2 = ffma2(ab, ab, q2);
+    }
+    *reinterpret_cast<float2*>(stat_dst + lane * 2) = make_float2(s2.x + s2.y, q2.x + q2.y);
+  }
+}
+
 template <int N, bool OUT_F32, bool CTA2>
 __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<N, CTA2>;
@@ -429,6 +471,7 @@ struct HaloParams {
   int tiles_h, tiles_w, num_tiles;
   const float* bias;
   float* stats;
+  float* out4;                   // OUT4 kernels: fp32 NHWC [B,H,W,4] written directly by the epilogue
   long long* dbg;                // optional [16] cycle counters written by block 0 (tools/halo_dbg.py)
   int xf_mode;                   // experiments (env FD_HALO_XF_MODE): 0 normal, 1 barriers only, 2 loads only, 3 no stores
 };
@@ -441,17 +484,24 @@ struct HaloParams {
 #define FD_DBG (FD_HALO_DEBUG && p.dbg != nullptr)
 #define FD_XF_MODE (FD_HALO_DEBUG ? p.xf_mode : 0)
 
-template <int N>
+// TF32: fp32 activations / weights in HBM and shared memory, kind::tf32 MMAs (K = 8 per instruction, 32 channels
+// per 128-byte k-slice: the byte geometry of boxes, swizzle and descriptors is identical to bf16), fp32 output.
+// OUT4: N = 16 accumulator columns of which 4 are real — the pyramid convs C -> 4 (ncsnpp.py:218,230) — written
+// by the epilogue as one float4 per pixel.
+template <int N, bool TF32, bool OUT4>
 struct HaloCfg {
   static constexpr int kStagesA = 3;
   static constexpr int kStagesB = 6;
-  static constexpr int kBBytes = (N / 2) * kSliceK * 2;
-  static constexpr int kOutBytes = 2 * kTileM * 128;
+  static constexpr int kSliceC = TF32 ? 32 : 64;          // channels per k-slice (128 bytes)
+  static constexpr int kBBytes = (N / 2) * 128;
+  static constexpr int kOutBytes = OUT4 ? 0 : 2 * kTileM * 128;
   static constexpr int kSsFloats = 2 * 512;   // scale/shift of up to 512 transformed channels
-  static constexpr int kTmemCols = (2 * N <= 256) ? 256 : 512;
-  static constexpr int kStatScratch = FD_EPI_STATS_SMEM ? 4 * 32 * 36 * 4 : 0;   // per epilogue warp: 32 x 36 floats
+  static constexpr int kTmemCols = (2 * N <= 32) ? 32 : ((2 * N <= 64) ? 64 : ((2 * N <= 128) ? 128 : ((2 * N <= 256) ? 256 : 512)));
+  static constexpr int kStatScratch = (FD_EPI_STATS_SMEM && !OUT4) ? 4 * 32 * 36 * 4 : 0;   // per epilogue warp: 32 x 36 floats
   static constexpr int kSmemBytes = 1024 + kStagesA * kHaloStageBytes + kStagesB * kBBytes + kOutBytes + N * 4 +
                                     kSsFloats * 4 + 512 + kStatScratch;
+  static_assert(kBBytes % 1024 == 0, "B stage must keep the 1024-byte swizzle alignment");
+  static_assert(!OUT4 || N == 16, "OUT4 is the N = 16 pyramid tile");
 };
 
 // Transform-warp placement.  FD_XF_LAYOUT 0 (default): warps 7..14 (two of them share the MMA warp's scheduler
@@ -463,10 +513,11 @@ struct HaloCfg {
 #endif
 constexpr int kHaloXfThreads = FD_XF_LAYOUT ? 544 : 480;
 
-template <int N, bool XF>
+template <int N, bool XF, bool TF32, bool OUT4>
 __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
-  using Cfg = HaloCfg<N>;
+  using Cfg = HaloCfg<N, TF32, OUT4>;
   constexpr int SA = Cfg::kStagesA, SB = Cfg::kStagesB, B_BYTES = Cfg::kBBytes;
+  constexpr int kSliceC = Cfg::kSliceC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -508,7 +559,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
     fence_mbar_init();
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.a_map[s]);
     tma_prefetch_desc(&p.b_map);
-    tma_prefetch_desc(&p.out_map);
+    if (!OUT4) tma_prefetch_desc(&p.out_map);
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
   tc_fence_before_sync();
@@ -536,11 +587,11 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
             mbar_wait(&emptyA[sa], pa ^ 1u);
             if (XF) {
               mbar_expect_tx(&fullA[sa], kHaloTxBytes);
-              tma_load_4d(sA + sa * kHaloStageBytes, &p.a_map[s], &fullA[sa], ks * kSliceK, w0 - 1, h0 - 1, n);
+              tma_load_4d(sA + sa * kHaloStageBytes, &p.a_map[s], &fullA[sa], ks * kSliceC, w0 - 1, h0 - 1, n);
             } else {
               if (leader_cta) mbar_expect_tx(&readyA[sa], 2 * kHaloTxBytes);
               else mbar_arrive_remote(&readyA[sa], 0);
-              tma_load_4d_2sm(sA + sa * kHaloStageBytes, &p.a_map[s], &readyA[sa], ks * kSliceK, w0 - 1, h0 - 1, n);
+              tma_load_4d_2sm(sA + sa * kHaloStageBytes, &p.a_map[s], &readyA[sa], ks * kSliceC, w0 - 1, h0 - 1, n);
             }
             if (++sa == SA) { sa = 0; pa ^= 1u; }
           }
@@ -557,7 +608,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           const int ntap = p.seg_taps[s];
           for (int ks = 0; ks < p.seg_kslices[s]; ++ks) {
             for (int tap = 0; tap < ntap; ++tap) {
-              const int kcol = p.seg_kbase[s] + tap * p.seg_cin[s] + ks * kSliceK;
+              const int kcol = p.seg_kbase[s] + tap * p.seg_cin[s] + ks * kSliceC;
               mbar_wait(&emptyB[sb], pb ^ 1u);
               if (leader_cta) mbar_expect_tx(&fullB[sb], 2 * B_BYTES);
               else mbar_arrive_remote(&fullB[sb], 0);
@@ -572,7 +623,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
     // ---------------------------------------------------------------- MMA issuer (leader CTA)
     // warp-uniform loop, one elected lane issues (descriptors stay in uniform registers)
     if (leader_cta) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * kTileM, N);
+      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(2 * kTileM, N) : umma_idesc_bf16(2 * kTileM, N);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int acc = 0, issued = 0;
@@ -610,9 +661,14 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
               const uint64_t db = umma_desc_k_sw128(smem_u32(sB + sb * B_BYTES));
               if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < kSliceK / 16; ++k)
-                  umma_bf16_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                                idesc, (first && k == 0) ? 0u : 1u);
+                for (int k = 0; k < 4; ++k) {     // four 32-byte K steps per 128-byte slice (K = 16 bf16 / 8 tf32)
+                  if (TF32)
+                    umma_tf32_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                                  idesc, (first && k == 0) ? 0u : 1u);
+                  else
+                    umma_bf16_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                                  idesc, (first && k == 0) ? 0u : 1u);
+                }
                 umma_commit_2sm(&emptyB[sb]);
                 if (tap == ntap - 1) {
                   umma_commit_2sm(&emptyA[sa]);
@@ -658,6 +714,46 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * N);
+      if constexpr (OUT4) {
+        // pyramid conv C -> 4: columns 0..3 of the 16-column accumulator, one float4 per pixel
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row, v);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive_remote(&tempty_bar[acc], 0);
+        const int hl = row >> 3, wl = row & 7;
+        float4 r;
+        r.x = __uint_as_float(v[0]) + sBias[0];
+        r.y = __uint_as_float(v[1]) + sBias[1];
+        r.z = __uint_as_float(v[2]) + sBias[2];
+        r.w = __uint_as_float(v[3]) + sBias[3];
+        *reinterpret_cast<float4*>(p.out4 + ((static_cast<size_t>(n) * p.H + (h0 + hl)) * p.W + (w0 + wl)) * 4) = r;
+      } else if constexpr (TF32) {
+        constexpr int kChunks = N / 32;           // 32 fp32 channels = one 128-byte staging row
+        const int slab = rem * 4 + ew;
+        float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * (tiles_per_img * 4) + slab) * N) * 2 : nullptr;
+#pragma unroll 1
+        for (int ch = 0; ch < kChunks; ++ch) {
+          uint8_t* stg = sOut + (ch & 1) * (kTileM * 128);
+          if (leader) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + ch * 32, v);
+          tmem_ld_wait();
+          if (ch == kChunks - 1) {
+            tc_fence_before_sync();
+            mbar_arrive_remote(&tempty_bar[acc], 0);
+          }
+          epilogue_chunk_f32(v, smem_u32(sBias + ch * 32), smem_u32(stg + row * 128), row,
+                             stat_row ? stat_row + (ch * 32) * 2 : nullptr, lane, stat_scratch);
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (leader) {
+            tma_store_4d(&p.out_map, stg, ch * 32, w0, h0, n);
+            tma_store_commit();
+          }
+        }
+      } else {
       constexpr int kChunks = N / 64;
       const int slab = rem * 4 + ew;
       float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * (tiles_per_img * 4) + slab) * N) * 2 : nullptr;
@@ -690,10 +786,11 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           tma_store_commit();
         }
       }
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (leader) tma_store_wait_all<0>();
+    if (!OUT4 && leader) tma_store_wait_all<0>();
   } else if (XF && warp >= 7 && !(FD_XF_LAYOUT && (warp & 3) == 1)) {
     // ---------------------------------------------------------------- transform warps (8 of them)
     const int tq = FD_XF_LAYOUT ? (warp - 7 - (warp > 9 ? 1 : 0) - (warp > 13 ? 1 : 0)) : (warp - 7);
@@ -747,10 +844,12 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           mbar_wait(&fullA[sa], pa);
           if (FD_DBG) { const long long now = clock64(); x_wait += now - xq; xq = now; }
           if (xf && FD_XF_MODE != 1) {
+            constexpr int kPairs = TF32 ? 2 : 4;    // channel pairs per 16-byte chunk
             float2 sc2[4], sh2[4];                  // (scale, shift) / 2 of channel pairs 2e, 2e+1
-            const uint32_t ss_addr = smem_u32(sSS) + static_cast<uint32_t>(p.seg_ss_off[s] + ks * kSliceK + j * 8) * 8u;
+            const uint32_t ss_addr = smem_u32(sSS) +
+                static_cast<uint32_t>(p.seg_ss_off[s] + ks * kSliceC + j * (2 * kPairs)) * 8u;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < kPairs; ++e) {
               const float4 q = lds_f4(ss_addr + e * 16);
               sc2[e] = make_float2(q.x, q.y);
               sh2[e] = make_float2(q.z, q.w);
@@ -782,10 +881,20 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
                     const uint32_t m = decltype(masked)::value ? 0u - ((okmask >> i) & 1u) : 0xffffffffu;
                     const uint32_t w4[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
                     uint32_t o4[4];
+                    if constexpr (TF32) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {          // two channels per packed fp32x2 operation
-                      const float2 y = silu2_from_half(ffma2(unpack_bf16x2(w4[e]), sc2[e], sh2[e]));
-                      o4[e] = m & pack_bf16x2(y.x, y.y);
+                      for (int e = 0; e < 2; ++e) {        // four fp32 channels per chunk, rounded (RN) to tf32
+                        const float2 x = make_float2(__uint_as_float(w4[2 * e]), __uint_as_float(w4[2 * e + 1]));
+                        const float2 y = silu2_from_half(ffma2(x, sc2[e], sh2[e]));
+                        o4[2 * e] = m & __float_as_uint(round_tf32(y.x));
+                        o4[2 * e + 1] = m & __float_as_uint(round_tf32(y.y));
+                      }
+                    } else {
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {        // two channels per packed fp32x2 operation
+                        const float2 y = silu2_from_half(ffma2(unpack_bf16x2(w4[e]), sc2[e], sh2[e]));
+                        o4[e] = m & pack_bf16x2(y.x, y.y);
+                      }
                     }
                     uint4 q = make_uint4(o4[0], o4[1], o4[2], o4[3]);
                     if (FD_XF_MODE != 3 || q.x == 0x12345678u) sts128(base + static_cast<uint32_t>(r) * 128u, q);
@@ -857,36 +966,38 @@ int device_sm_count() {
 }
 
 // NHWC bf16 tensor [B,H,W,Ctot]; the map exposes channels [c_begin, c_begin + c_count)
+// (f32: fp32 elements, 32 channels per 128-byte box row — the tf32 kernels)
 static int make_nhwc_map(CUtensorMap* m, const void* base, int B, int H, int W, int Ctot,
-                         int c_begin, int c_count, int bh, int bw) {
+                         int c_begin, int c_count, int bh, int bw, bool f32 = false) {
   EncodeTiledFn enc = get_encode_fn();
   FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  const size_t el = f32 ? 4 : 2;
   FD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (c_begin % 8) == 0 && (Ctot % 8) == 0,
              "NHWC tensor must be 16-byte aligned with channel counts that are multiples of 8");
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(c_count), static_cast<cuuint64_t>(W),
                         static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(Ctot) * 2,
-                           static_cast<cuuint64_t>(W) * Ctot * 2,
-                           static_cast<cuuint64_t>(H) * W * Ctot * 2};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(kSliceK), static_cast<cuuint32_t>(bw),
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(Ctot) * el,
+                           static_cast<cuuint64_t>(W) * Ctot * el,
+                           static_cast<cuuint64_t>(H) * W * Ctot * el};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(f32 ? 32 : kSliceK), static_cast<cuuint32_t>(bw),
                        static_cast<cuuint32_t>(bh), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  void* addr = const_cast<uint8_t*>(static_cast<const uint8_t*>(base)) + static_cast<size_t>(c_begin) * 2;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, addr, dims, strides, box, estr,
+  void* addr = const_cast<uint8_t*>(static_cast<const uint8_t*>(base)) + static_cast<size_t>(c_begin) * el;
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, addr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(NHWC) failed with CUresult %d", (int)r);
   return 0;
 }
 
-static int make_weight_map(CUtensorMap* m, const void* base, int npad, int ktot, int box_rows) {
+static int make_weight_map(CUtensorMap* m, const void* base, int npad, int ktot, int box_rows, bool f32 = false) {
   EncodeTiledFn enc = get_encode_fn();
   FD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(npad)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kSliceK), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(f32 ? 32 : kSliceK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
@@ -925,10 +1036,10 @@ static int launch_conv(const ConvParams& p, int max_ctas, cudaStream_t stream) {
   return check_launch("fd_conv2d_igemm");
 }
 
-template <int N, bool XF>
+template <int N, bool XF, bool TF32 = false, bool OUT4 = false>
 static int launch_halo(const HaloParams& p, int max_ctas, cudaStream_t stream) {
-  auto kern = conv_halo_kernel<N, XF>;
-  using Cfg = HaloCfg<N>;
+  auto kern = conv_halo_kernel<N, XF, TF32, OUT4>;
+  using Cfg = HaloCfg<N, TF32, OUT4>;
   static bool attr_set[kMaxDevices] = {false};   // function attributes are per device
   const int dev = current_device();
   if (!attr_set[dev]) {
@@ -984,38 +1095,36 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
   const int bh = kTileM / bw;
   FD_REQUIRE(H % bh == 0, "fd_conv2d_igemm: H=%d not divisible by tile height %d", H, bh);
 
-  ConvParams p;
-  memset(&p, 0, sizeof(p));
-  p.nseg = nsrc;
+  const bool tf32 = (flags & 4) != 0;      // fp32 activations + weights, kind::tf32 MMAs (halo kernels only)
+  const int slice = tf32 ? 32 : kSliceK;
   int ksum = 0;
   for (int s = 0; s < nsrc; ++s) {
     FD_REQUIRE(srcs[s].taps == 1 || srcs[s].taps == 9, "fd_conv2d_igemm: taps must be 1 or 9");
-    FD_REQUIRE(srcs[s].c_count % kSliceK == 0 && srcs[s].c_count > 0,
-               "fd_conv2d_igemm: segment channel count %d not a multiple of 64", srcs[s].c_count);
-    p.seg_kslices[s] = srcs[s].c_count / kSliceK;
-    p.seg_taps[s] = srcs[s].taps;
+    FD_REQUIRE(srcs[s].c_count % slice == 0 && srcs[s].c_count > 0,
+               "fd_conv2d_igemm: segment channel count %d not a multiple of %d", srcs[s].c_count, slice);
     ksum += srcs[s].c_count * srcs[s].taps;
-    if (make_nhwc_map(&p.a_map[s], srcs[s].ptr, B, H, W, srcs[s].C, srcs[s].c_begin,
-                      srcs[s].c_count, bh, bw))
-      return 1;
   }
   FD_REQUIRE(ksum == ktot, "fd_conv2d_igemm: packed K=%d does not match segments (%d)", ktot, ksum);
   bool any_xf = false;
   for (int s = 0; s < nsrc; ++s) any_xf = any_xf || (srcs[s].scale_shift != nullptr);
   {
-    // "halo" kernel: 8x16 tiles, A box shared by the three vertical taps, optional fused GN+SiLU
-    const bool halo_ok = !out_is_f32 && (flags & 1) && (flags & 2) && (npad == 128 || npad == 256) &&
-                         (W % kHaloTileW == 0) && (H % kHaloTileH == 0) &&
+    // "halo" kernel: 16x8 tiles, one A box per k-slice for all nine taps, optional fused GN+SiLU, optional tf32,
+    // optional 4-channel fp32 output (pyramid convs)
+    const bool out4 = out_is_f32 && npad == 16 && cout == 4;
+    const bool geom_ok = (flags & 1) && (flags & 2) && (W % kHaloTileW == 0) && (H % kHaloTileH == 0) &&
                          ((static_cast<long long>(B) * (H / kHaloTileH) * (W / kHaloTileW)) % 2 == 0);
+    const bool halo_ok = geom_ok && (out4 || ((npad == 128 || npad == 256) && (out_is_f32 != 0) == tf32));
     FD_REQUIRE(halo_ok || !any_xf, "fd_conv2d_igemm: fused GroupNorm+SiLU needs the halo kernel "
-               "(bf16 out, flags 3, W %% 8 == 0, H %% 16 == 0, even tile count)");
+               "(flags 3, W %% 8 == 0, H %% 16 == 0, even tile count)");
+    FD_REQUIRE(halo_ok || !tf32, "fd_conv2d_igemm: tf32 (flags bit 2) needs the halo kernel "
+               "(flags 7, fp32 output, npad 128/256 or the 4-channel form, W %% 8 == 0, H %% 16 == 0, even tile count)");
     if (halo_ok) {
       HaloParams hp;
       memset(&hp, 0, sizeof(hp));
       hp.nseg = nsrc;
       int kb = 0, ssoff = 0;
       for (int s = 0; s < nsrc; ++s) {
-        hp.seg_kslices[s] = srcs[s].c_count / kSliceK;
+        hp.seg_kslices[s] = srcs[s].c_count / slice;
         hp.seg_taps[s] = srcs[s].taps;
         hp.seg_kbase[s] = kb;
         hp.seg_cin[s] = srcs[s].c_count;
@@ -1025,13 +1134,18 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
         if (srcs[s].scale_shift) ssoff += srcs[s].c_count;
         kb += srcs[s].c_count * srcs[s].taps;
         if (make_nhwc_map(&hp.a_map[s], srcs[s].ptr, B, H, W, srcs[s].C, srcs[s].c_begin, srcs[s].c_count,
-                          kHaloRows, kHaloCols))
+                          kHaloRows, kHaloCols, tf32))
           return 1;
       }
       FD_REQUIRE(ssoff <= 512, "fd_conv2d_igemm: at most 512 transformed channels (got %d)", ssoff);
-      if (make_weight_map(&hp.b_map, wpacked, npad, ktot, npad / 2)) return 1;
-      FD_REQUIRE(cout == npad, "fd_conv2d_igemm: bf16 output needs cout == npad");
-      if (make_nhwc_map(&hp.out_map, out, B, H, W, cout, 0, cout, kHaloTileH, kHaloTileW)) return 1;
+      if (make_weight_map(&hp.b_map, wpacked, npad, ktot, npad / 2, tf32)) return 1;
+      if (!out4) {
+        FD_REQUIRE(cout == npad, "fd_conv2d_igemm: NHWC output needs cout == npad");
+        if (make_nhwc_map(&hp.out_map, out, B, H, W, cout, 0, cout, kHaloTileH, kHaloTileW, tf32)) return 1;
+      } else {
+        FD_REQUIRE(stats == nullptr, "fd_conv2d_igemm: no statistics for the 4-channel output");
+        hp.out4 = static_cast<float*>(out);
+      }
       hp.B = B;
       hp.H = H;
       hp.W = W;
@@ -1046,10 +1160,33 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
         const char* m = getenv("FD_HALO_XF_MODE");
         hp.xf_mode = m ? atoi(m) : 0;
       }
+      if (out4) {
+        if (tf32) return any_xf ? launch_halo<16, true, true, true>(hp, max_ctas, stream)
+                                : launch_halo<16, false, true, true>(hp, max_ctas, stream);
+        return any_xf ? launch_halo<16, true, false, true>(hp, max_ctas, stream)
+                      : launch_halo<16, false, false, true>(hp, max_ctas, stream);
+      }
+      if (tf32) {
+        if (npad == 256) return any_xf ? launch_halo<256, true, true>(hp, max_ctas, stream)
+                                       : launch_halo<256, false, true>(hp, max_ctas, stream);
+        return any_xf ? launch_halo<128, true, true>(hp, max_ctas, stream)
+                      : launch_halo<128, false, true>(hp, max_ctas, stream);
+      }
       if (npad == 256) return any_xf ? launch_halo<256, true>(hp, max_ctas, stream)
                                      : launch_halo<256, false>(hp, max_ctas, stream);
       return any_xf ? launch_halo<128, true>(hp, max_ctas, stream) : launch_halo<128, false>(hp, max_ctas, stream);
     }
+  }
+  // ---- per-tap kernel (bf16 only)
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.nseg = nsrc;
+  for (int s = 0; s < nsrc; ++s) {
+    p.seg_kslices[s] = srcs[s].c_count / kSliceK;
+    p.seg_taps[s] = srcs[s].taps;
+    if (make_nhwc_map(&p.a_map[s], srcs[s].ptr, B, H, W, srcs[s].C, srcs[s].c_begin,
+                      srcs[s].c_count, bh, bw))
+      return 1;
   }
   // CTA pairs (cta_group::2, M = 256 per MMA) for the bf16-output tiles when the tile count is even
   const bool pair = !out_is_f32 && ((flags & 1) != 0) && (((B * (H / bh) * (W / bw)) & 1) == 0) &&

@@ -9,6 +9,8 @@
 //
 // Layouts: activations bf16 NHWC [B,H,W,C]; 4-channel pyramids fp32 [B,H,W,4]; ODE state and
 // spectrograms float2 [B,F,T] (bit-identical to complex64 [B,1,F,T]).
+#include <type_traits>
+
 #include "fd_common.cuh"
 
 namespace fd {
@@ -36,11 +38,23 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = r;
 }
 
+// fp32 activations (tf32 "precise" mode): the same helpers on float pointers
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 // ------------------------------------------------------------------------------------------
 // per-(sample, channel) sum / sum-of-squares, deterministic two-level reduction
 //   partial[b][s][c][2]  (fp32), s = slab index; finalize reduces slabs in fp64
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) chan_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW,
+template <typename T>
+__global__ void __launch_bounds__(256) chan_stats_kernel(const T* __restrict__ x, int HW,
                                                          int C, float* __restrict__ partial, int S) {
   extern __shared__ float red[];  // [256][16]
   const int b = blockIdx.y, s = blockIdx.x;
@@ -54,7 +68,7 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const __nv_bfloat16* __
   float sum[8], sq[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
-  const __nv_bfloat16* base = x + static_cast<size_t>(b) * HW * C + o * 8;
+  const T* base = x + static_cast<size_t>(b) * HW * C + o * 8;
   if (pl < ppi) {
     for (int p = p0 + pl; p < p1; p += ppi) {
       float v[8];
@@ -168,9 +182,9 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
 //   MODE 0: unit = 1 pixel;  MODE 1: unit = 2x2 output patch (6x6 inputs, each activated once);
 //   MODE 2: unit = 1 input pixel -> 2x2 output quad (3x3 inputs).
 // ------------------------------------------------------------------------------------------
-template <int CPT>
+template <int CPT, typename T = __nv_bfloat16>
 struct ChanSlice {
-  const __nv_bfloat16* img;  // source image base (+ channel offset) of this sample
+  const T* img;              // source image base (+ channel offset) of this sample
   int Cs;                    // channel pitch of that source
   float sc[CPT], sh[CPT];
 };
@@ -186,6 +200,14 @@ __device__ __forceinline__ void loadN(const __nv_bfloat16* p, float (&v)[CPT]) {
   }
 }
 
+__device__ __forceinline__ void loadN(const float* p, float (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void storeN(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 template <int CPT>
 __device__ __forceinline__ void storeN(__nv_bfloat16* p, const float (&v)[CPT]) {
   if constexpr (CPT == 8) {
@@ -198,8 +220,13 @@ __device__ __forceinline__ void storeN(__nv_bfloat16* p, const float (&v)[CPT]) 
   }
 }
 
-template <bool ACT, int CPT>
-__device__ __forceinline__ void load_act(const ChanSlice<CPT>& o, int H, int W, int hi, int wi,
+template <int CPT>
+__device__ __forceinline__ void store_any(__nv_bfloat16* p, const float (&v)[CPT]) { storeN<CPT>(p, v); }
+template <int CPT>
+__device__ __forceinline__ void store_any(float* p, const float (&v)[CPT]) { storeN(p, v); }
+
+template <bool ACT, int CPT, typename T>
+__device__ __forceinline__ void load_act(const ChanSlice<CPT, T>& o, int H, int W, int hi, int wi,
                                          float (&a)[CPT], float (&r)[CPT], bool want_raw) {
   if (hi < 0 || hi >= H || wi < 0 || wi >= W) {
 #pragma unroll
@@ -207,7 +234,8 @@ __device__ __forceinline__ void load_act(const ChanSlice<CPT>& o, int H, int W, 
     return;
   }
   float v[CPT];
-  loadN<CPT>(o.img + (static_cast<size_t>(hi) * W + wi) * o.Cs, v);
+  if constexpr (std::is_same<T, float>::value) loadN(o.img + (static_cast<size_t>(hi) * W + wi) * o.Cs, v);
+  else loadN<CPT>(o.img + (static_cast<size_t>(hi) * W + wi) * o.Cs, v);
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
     if (want_raw) r[i] = v[i];
@@ -219,11 +247,11 @@ __device__ __forceinline__ void load_act(const ChanSlice<CPT>& o, int H, int W, 
 // enough for >= 3 blocks per SM) of one unit:
 //   MODE 1: unit = 2x2 output patch (6x6 inputs, each activated once);
 //   MODE 2: unit = 1 input pixel -> 2x2 output quad (3x3 inputs).
-template <int MODE, bool ACT, bool RAW>
+template <int MODE, bool ACT, bool RAW, typename T>
 __global__ void __launch_bounds__(256) gn_act_resample_kernel(
-    const __nv_bfloat16* __restrict__ src1, int C1, const __nv_bfloat16* __restrict__ src2, int C2,
-    const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ out,
-    __nv_bfloat16* __restrict__ out_raw, int H, int W) {
+    const T* __restrict__ src1, int C1, const T* __restrict__ src2, int C2,
+    const float* __restrict__ scale_shift, T* __restrict__ out,
+    T* __restrict__ out_raw, int H, int W) {
   constexpr int CPT = 4;
   const int C = C1 + C2;
   const int slices = C / CPT;
@@ -236,7 +264,7 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
   if (t >= UW * slices) return;
   const int uw = t / slices;
   const int c0 = (t - uw * slices) * CPT;
-  ChanSlice<CPT> o;
+  ChanSlice<CPT, T> o;
   {
     const bool first = c0 < C1;
     o.Cs = first ? C1 : C2;
@@ -270,7 +298,7 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
 #pragma unroll
       for (int ci = 0; ci < 6; ++ci) {
         float a[CPT], r[CPT];
-        load_act<ACT, CPT>(o, H, W, hi, 4 * uw - 1 + ci, a, r, RAW);
+        load_act<ACT, CPT, T>(o, H, W, hi, 4 * uw - 1 + ci, a, r, RAW);
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           if (ci < 4) { h0[c] = fmaf(k[ci], a[c], h0[c]); if (RAW) rh0[c] = fmaf(k[ci], r[c], rh0[c]); }
@@ -296,8 +324,8 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const size_t off = ((static_cast<size_t>(b) * Ho + 2 * row_unit + i) * Wo + 2 * uw + j) * C + c0;
-        storeN<CPT>(out + off, acc[i][j]);
-        if (RAW) storeN<CPT>(out_raw + off, racc[i][j]);
+        store_any<CPT>(out + off, acc[i][j]);
+        if (RAW) store_any<CPT>(out_raw + off, racc[i][j]);
       }
   } else {
     // input pixel (row_unit, uw) -> outputs (2*row_unit + {0,1}, 2*uw + {0,1})
@@ -306,9 +334,9 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
 #pragma unroll
     for (int cj = 0; cj < 3; ++cj) {
       float a0[CPT], a1[CPT], a2[CPT], r0[CPT], r1[CPT], r2[CPT];
-      load_act<ACT, CPT>(o, H, W, row_unit - 1, uw - 1 + cj, a0, r0, RAW);
-      load_act<ACT, CPT>(o, H, W, row_unit, uw - 1 + cj, a1, r1, RAW);
-      load_act<ACT, CPT>(o, H, W, row_unit + 1, uw - 1 + cj, a2, r2, RAW);
+      load_act<ACT, CPT, T>(o, H, W, row_unit - 1, uw - 1 + cj, a0, r0, RAW);
+      load_act<ACT, CPT, T>(o, H, W, row_unit, uw - 1 + cj, a1, r1, RAW);
+      load_act<ACT, CPT, T>(o, H, W, row_unit + 1, uw - 1 + cj, a2, r2, RAW);
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         top[cj][c] = 0.25f * a0[c] + 0.75f * a1[c];
@@ -338,11 +366,11 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
         }
       }
       const size_t off = ((static_cast<size_t>(b) * Ho + 2 * row_unit + i) * Wo + 2 * uw) * C + c0;
-      storeN<CPT>(out + off, e);
-      storeN<CPT>(out + off + C, f);
+      store_any<CPT>(out + off, e);
+      store_any<CPT>(out + off + C, f);
       if (RAW) {
-        storeN<CPT>(out_raw + off, re);
-        storeN<CPT>(out_raw + off + C, rf);
+        store_any<CPT>(out_raw + off, re);
+        store_any<CPT>(out_raw + off + C, rf);
       }
     }
   }
@@ -351,11 +379,11 @@ __global__ void __launch_bounds__(256) gn_act_resample_kernel(
 // MODE 0 specialisation: a = SiLU(x*scale+shift), same resolution.  A thread owns one channel
 // octet (scale/shift in registers) and walks kPix pixels spaced one block-row apart, so the 64 B
 // of per-channel parameters are loaded once per 8 x 16 B of activations.
-template <int kPix>
-__global__ void __launch_bounds__(256) gn_act_kernel(const __nv_bfloat16* __restrict__ src1, int C1,
-                                                     const __nv_bfloat16* __restrict__ src2, int C2,
+template <int kPix, typename T>
+__global__ void __launch_bounds__(256) gn_act_kernel(const T* __restrict__ src1, int C1,
+                                                     const T* __restrict__ src2, int C2,
                                                      const float* __restrict__ scale_shift,
-                                                     __nv_bfloat16* __restrict__ out, int HW) {
+                                                     T* __restrict__ out, int HW) {
   const int C = C1 + C2;
   const int oct = C >> 3;
   const int ppb = 256 / oct;               // pixels covered by one block pass
@@ -366,7 +394,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const __nv_bfloat16* __rest
   const int c0 = o8 * 8;
   const bool first = c0 < C1;
   const int Cs = first ? C1 : C2;
-  const __nv_bfloat16* img = (first ? src1 : src2) + static_cast<size_t>(b) * HW * Cs + (first ? c0 : c0 - C1);
+  const T* img = (first ? src1 : src2) + static_cast<size_t>(b) * HW * Cs + (first ? c0 : c0 - C1);
   float sc[8], sh[8];
   const float4* ss = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(b) * C + c0) * 2);
 #pragma unroll
@@ -375,23 +403,36 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const __nv_bfloat16* __rest
     sc[2 * i] = q.x; sh[2 * i] = q.y; sc[2 * i + 1] = q.z; sh[2 * i + 1] = q.w;
   }
   const int p0 = blockIdx.x * (ppb * kPix) + pl;
-  uint4 raw[kPix];
+  T* ob = out + static_cast<size_t>(b) * HW * C + c0;
+  if constexpr (std::is_same<T, float>::value) {
 #pragma unroll
-  for (int j = 0; j < kPix; ++j) {
-    const int p = p0 + j * ppb;
-    if (p < HW) raw[j] = *reinterpret_cast<const uint4*>(img + static_cast<size_t>(p) * Cs);
-  }
-  __nv_bfloat16* ob = out + static_cast<size_t>(b) * HW * C + c0;
+    for (int j = 0; j < kPix; ++j) {
+      const int p = p0 + j * ppb;
+      if (p >= HW) continue;
+      float v[8];
+      load8(img + static_cast<size_t>(p) * Cs, v);
 #pragma unroll
-  for (int j = 0; j < kPix; ++j) {
-    const int p = p0 + j * ppb;
-    if (p >= HW) continue;
-    const float2 a = unpack_bf16x2(raw[j].x), bq = unpack_bf16x2(raw[j].y), c = unpack_bf16x2(raw[j].z),
-                 d = unpack_bf16x2(raw[j].w);
-    float v[8] = {a.x, a.y, bq.x, bq.y, c.x, c.y, d.x, d.y};
+      for (int i = 0; i < 8; ++i) v[i] = silu_f(fmaf(v[i], sc[i], sh[i]));
+      store8(ob + static_cast<size_t>(p) * C, v);
+    }
+  } else {
+    uint4 raw[kPix];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = silu_f(fmaf(v[i], sc[i], sh[i]));
-    store8(ob + static_cast<size_t>(p) * C, v);
+    for (int j = 0; j < kPix; ++j) {
+      const int p = p0 + j * ppb;
+      if (p < HW) raw[j] = *reinterpret_cast<const uint4*>(img + static_cast<size_t>(p) * Cs);
+    }
+#pragma unroll
+    for (int j = 0; j < kPix; ++j) {
+      const int p = p0 + j * ppb;
+      if (p >= HW) continue;
+      const float2 a = unpack_bf16x2(raw[j].x), bq = unpack_bf16x2(raw[j].y), c = unpack_bf16x2(raw[j].z),
+                   d = unpack_bf16x2(raw[j].w);
+      float v[8] = {a.x, a.y, bq.x, bq.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = silu_f(fmaf(v[i], sc[i], sh[i]));
+      store8(ob + static_cast<size_t>(p) * C, v);
+    }
   }
 }
 
@@ -519,10 +560,11 @@ __global__ void pyramid_gather_kernel(const float* __restrict__ part, int pc, co
 // two adjacent pixels x 8 channels so every LDS.128 of weights feeds 8 FMAs.
 // smem weights: [tap][ci][64]
 // ------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float4* __restrict__ in,
                                                       const float* __restrict__ w,
                                                       const float* __restrict__ bias,
-                                                      __nv_bfloat16* __restrict__ out, int B, int H,
+                                                      T* __restrict__ out, int B, int H,
                                                       int W) {
   __shared__ __align__(16) float sw[36][64];
   __shared__ float sb[64];
@@ -575,7 +617,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float4* __restrict__
         }
       }
     }
-    __nv_bfloat16* op = out + ((static_cast<size_t>(b) * H + h) * W + wx) * 64 + o * 8;
+    T* op = out + ((static_cast<size_t>(b) * H + h) * W + wx) * 64 + o * 8;
     store8(op, acc0);
     if (wx + 1 < W) store8(op + 64, acc1);
   }
@@ -583,11 +625,12 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float4* __restrict__
 
 // Combine(method='sum'): out = h + Conv1x1_{4->C}(pyr) + bias   (layerspp.py:62-69)
 // thread = one channel octet (weights held in registers) walking pixels with the block stride
+template <typename T>
 __global__ void __launch_bounds__(256) combine_kernel(const float4* __restrict__ pyr,
                                                       const float* __restrict__ w,   // [C][4]
                                                       const float* __restrict__ bias,
-                                                      const __nv_bfloat16* __restrict__ h,
-                                                      __nv_bfloat16* __restrict__ out, int npix,
+                                                      const T* __restrict__ h,
+                                                      T* __restrict__ out, int npix,
                                                       int C) {
   const int oct = C >> 3;
   const int o = threadIdx.x % oct;
@@ -717,13 +760,24 @@ int fir_tiles_set(int on);
 extern "C" int fd_fir_tiles_enable(int on) { return fir_tiles_set(on); }
 typedef __nv_bfloat16 bf16;
 
-extern "C" int fd_chan_stats(const void* x, int B, int HW, int C, float* partial, int S,
-                             cudaStream_t stream) {
+template <typename T>
+static int chan_stats_launch(const void* x, int B, int HW, int C, float* partial, int S, cudaStream_t stream) {
   FD_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, "fd_chan_stats: unsupported C=%d", C);
   FD_REQUIRE(S >= 1, "fd_chan_stats: S must be >= 1");
-  chan_stats_kernel<<<dim3(S, B), 256, 256 * 16 * sizeof(float), stream>>>(
-      static_cast<const bf16*>(x), HW, C, partial, S);
+  chan_stats_kernel<T><<<dim3(S, B), 256, 256 * 16 * sizeof(float), stream>>>(
+      static_cast<const T*>(x), HW, C, partial, S);
   return check_launch("fd_chan_stats");
+}
+
+extern "C" int fd_chan_stats(const void* x, int B, int HW, int C, float* partial, int S,
+                             cudaStream_t stream) {
+  return chan_stats_launch<bf16>(x, B, HW, C, partial, S, stream);
+}
+
+// the `_f32` entry points take fp32 NHWC activations (tf32 "precise" mode of the backbone); same contracts
+extern "C" int fd_chan_stats_f32(const void* x, int B, int HW, int C, float* partial, int S,
+                                 cudaStream_t stream) {
+  return chan_stats_launch<float>(x, B, HW, C, partial, S, stream);
 }
 
 extern "C" int fd_slab_reduce(const float* in, int B, int S, int C, float* out, int chunks,
@@ -742,7 +796,8 @@ extern "C" int fd_gn_finalize(const float* part1, int C1, int S1, const float* p
   return check_launch("fd_gn_finalize");
 }
 
-extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, int C2,
+template <typename T>
+static int gn_act_resample_launch(const void* src1, int C1, const void* src2, int C2,
                                   const float* scale_shift, void* out, void* out_raw, int B, int H,
                                   int W, int mode, cudaStream_t stream) {
   FD_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0, "fd_gn_act_resample: channels must be multiples of 8");
@@ -751,7 +806,7 @@ extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, in
   FD_REQUIRE(out != nullptr || out_raw != nullptr, "fd_gn_act_resample: no output");
   FD_REQUIRE(out == nullptr || scale_shift != nullptr, "fd_gn_act_resample: activated output needs scale_shift");
   FD_REQUIRE(mode != 0 || out != nullptr, "fd_gn_act_resample: mode 0 without activation is a copy");
-  if (out != nullptr && out_raw != nullptr && fir_tiles_eligible(C1, C2, H, W, mode))
+  if (std::is_same<T, bf16>::value && out != nullptr && out_raw != nullptr && fir_tiles_eligible(C1, C2, H, W, mode))
     return fir_tiles_launch(src1, C1, src2, C2, scale_shift, out, out_raw, B, H, W, mode, stream);
   const int oct = (C1 + C2) / 8;
   const int slices = (C1 + C2) / 4;   // FIR variants: 4 channels per thread
@@ -760,12 +815,12 @@ extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, in
   FD_REQUIRE(static_cast<long long>(B) * UH <= 65535 && oct <= 256,
              "fd_gn_act_resample: B*rows=%lld exceeds grid.y (or C > 2048)", static_cast<long long>(B) * UH);
   dim3 grid((UW * slices + 255) / 256, B * UH);
-  const bf16* s1 = static_cast<const bf16*>(src1);
-  const bf16* s2 = static_cast<const bf16*>(src2);
-  bf16* o = static_cast<bf16*>(out);
-  bf16* r = static_cast<bf16*>(out_raw);
+  const T* s1 = static_cast<const T*>(src1);
+  const T* s2 = static_cast<const T*>(src2);
+  T* o = static_cast<T*>(out);
+  T* r = static_cast<T*>(out_raw);
 #define FD_LAUNCH_GN(M, A, R) \
-  gn_act_resample_kernel<M, A, R><<<grid, 256, 0, stream>>>(s1, C1, s2, C2, scale_shift, A ? o : r, r, H, W)
+  gn_act_resample_kernel<M, A, R, T><<<grid, 256, 0, stream>>>(s1, C1, s2, C2, scale_shift, A ? o : r, r, H, W)
   if (o != nullptr && r != nullptr) {
     if (mode == 1) FD_LAUNCH_GN(1, true, true);
     else if (mode == 2) FD_LAUNCH_GN(2, true, true);
@@ -775,7 +830,7 @@ extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, in
       const int ppb = 256 / oct;
       constexpr int kPix = 8;
       dim3 g0((H * W + ppb * kPix - 1) / (ppb * kPix), B);
-      gn_act_kernel<kPix><<<g0, 256, 0, stream>>>(s1, C1, s2, C2, scale_shift, o, H * W);
+      gn_act_kernel<kPix, T><<<g0, 256, 0, stream>>>(s1, C1, s2, C2, scale_shift, o, H * W);
     } else if (mode == 1) FD_LAUNCH_GN(1, true, false);
     else FD_LAUNCH_GN(2, true, false);
   } else {
@@ -784,6 +839,18 @@ extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, in
   }
 #undef FD_LAUNCH_GN
   return check_launch("fd_gn_act_resample");
+}
+
+extern "C" int fd_gn_act_resample(const void* src1, int C1, const void* src2, int C2,
+                                  const float* scale_shift, void* out, void* out_raw, int B, int H,
+                                  int W, int mode, cudaStream_t stream) {
+  return gn_act_resample_launch<bf16>(src1, C1, src2, C2, scale_shift, out, out_raw, B, H, W, mode, stream);
+}
+
+extern "C" int fd_gn_act_resample_f32(const void* src1, int C1, const void* src2, int C2,
+                                      const float* scale_shift, void* out, void* out_raw, int B, int H,
+                                      int W, int mode, cudaStream_t stream) {
+  return gn_act_resample_launch<float>(src1, C1, src2, C2, scale_shift, out, out_raw, B, H, W, mode, stream);
 }
 
 extern "C" int fd_pack4(const void* x, const void* y, void* out, size_t npix, cudaStream_t stream) {
@@ -821,9 +888,19 @@ extern "C" int fd_conv_in(const void* in4, const float* w, const float* bias, vo
   const size_t ntiles = static_cast<size_t>(B) * H * ((W + 63) / 64);
   FD_REQUIRE(ntiles < (1u << 31), "fd_conv_in: too many tiles");
   const int grid = static_cast<int>(ntiles < 148 * 8 ? ntiles : 148 * 8);
-  conv_in_kernel<<<grid, 256, 0, stream>>>(static_cast<const float4*>(in4), w, bias,
-                                           static_cast<bf16*>(out), B, H, W);
+  conv_in_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const float4*>(in4), w, bias,
+                                                 static_cast<bf16*>(out), B, H, W);
   return check_launch("fd_conv_in");
+}
+
+extern "C" int fd_conv_in_f32(const void* in4, const float* w, const float* bias, void* out, int B, int H,
+                              int W, cudaStream_t stream) {
+  const size_t ntiles = static_cast<size_t>(B) * H * ((W + 63) / 64);
+  FD_REQUIRE(ntiles < (1u << 31), "fd_conv_in_f32: too many tiles");
+  const int grid = static_cast<int>(ntiles < 148 * 8 ? ntiles : 148 * 8);
+  conv_in_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float4*>(in4), w, bias,
+                                                  static_cast<float*>(out), B, H, W);
+  return check_launch("fd_conv_in_f32");
 }
 
 extern "C" int fd_combine(const void* pyr4, const float* w, const float* bias, const void* h, void* out,
@@ -831,10 +908,20 @@ extern "C" int fd_combine(const void* pyr4, const float* w, const float* bias, c
   FD_REQUIRE(C % 8 == 0, "fd_combine: C=%d", C);
   FD_REQUIRE(C <= 2048 && npix < (1u << 31), "fd_combine: C=%d / npix out of range", C);
   const int ppb = 256 / (C / 8);
-  combine_kernel<<<grid_for((npix + ppb - 1) / ppb, 1), 256, 0, stream>>>(
+  combine_kernel<bf16><<<grid_for((npix + ppb - 1) / ppb, 1), 256, 0, stream>>>(
       static_cast<const float4*>(pyr4), w, bias, static_cast<const bf16*>(h), static_cast<bf16*>(out),
       static_cast<int>(npix), C);
   return check_launch("fd_combine");
+}
+
+extern "C" int fd_combine_f32(const void* pyr4, const float* w, const float* bias, const void* h, void* out,
+                              size_t npix, int C, cudaStream_t stream) {
+  FD_REQUIRE(C % 8 == 0 && C <= 2048 && npix < (1u << 31), "fd_combine_f32: C=%d / npix out of range", C);
+  const int ppb = 256 / (C / 8);
+  combine_kernel<float><<<grid_for((npix + ppb - 1) / ppb, 1), 256, 0, stream>>>(
+      static_cast<const float4*>(pyr4), w, bias, static_cast<const float*>(h), static_cast<float*>(out),
+      static_cast<int>(npix), C);
+  return check_launch("fd_combine_f32");
 }
 
 extern "C" int fd_output_axpy(const void* pyr4, const float* w_out_host8, const void* base1, float c1,

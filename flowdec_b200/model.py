@@ -61,6 +61,14 @@ class EnhancementModel(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    def set_precision(self, precision):
+        """"bf16" (default, the benchmarked mode) or "tf32" (fp32 activations, tf32 tensor-core operands: the
+        precision class of the reference's own GPU path); see NCSNpp.set_precision"""
+        if hasattr(self, "reset_cache"):
+            self.reset_cache()
+        self.backbone.set_precision(precision)
+        return self
+
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path, map_location=None, ema=True, build_fn=None, **kwargs):
         """What the reference intends (model.py:352-385, commented out there): build the model, then

@@ -17,21 +17,28 @@ HALO_TILES = True
 
 
 def halo_eligible(B, H, W, npad):
-    """mirror of the dispatch rule in fd_conv2d_igemm"""
-    return (CTA_PAIRS and HALO_TILES and npad in (128, 256) and W % 8 == 0 and H % 16 == 0
+    """mirror of the dispatch rule in fd_conv2d_igemm (npad 16 = the 4-channel fp32 pyramid form)"""
+    return (CTA_PAIRS and HALO_TILES and npad in (16, 128, 256) and W % 8 == 0 and H % 16 == 0
             and (B * (H // 16) * (W // 8)) % 2 == 0)
+
+
+def round_tf32(w):
+    """fp32 -> nearest tf32 (10-bit mantissa) kept in fp32 words; weights are rounded once at pack time, the
+    tensor pipe would otherwise truncate them"""
+    i = w.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 # when set to a list, conv_igemm appends (start_event, end_event, algorithmic_flops) per launch
 # (bench.py's roofline leg; events are recorded on the launching stream)
 PROFILE = None
 
 
-def pack_conv_weight(segments, npad):
+def pack_conv_weight(segments, npad, tf32=False):
     """Pack conv weights for fd_conv2d_igemm.
 
     segments: list of (w[Cout, Cin_seg, kh, kw], taps) in the K order the kernel walks:
-    for segment: for tap (kh-major): for channel.  Returns bf16 [npad, Ktot] (K-major),
-    rows >= Cout zero-filled.
+    for segment: for tap (kh-major): for channel.  Returns bf16 (or, tf32=True, tf32-rounded fp32)
+    [npad, Ktot] (K-major), rows >= Cout zero-filled.
     """
     cols = []
     cout = segments[0][0].shape[0]
@@ -39,7 +46,8 @@ def pack_conv_weight(segments, npad):
         assert w.shape[0] == cout and w.shape[2] * w.shape[3] == taps
         # [Cout, Cin, kh, kw] -> [Cout, kh, kw, Cin] -> [Cout, taps*Cin]
         cols.append(w.permute(0, 2, 3, 1).reshape(cout, -1))
-    wp = torch.cat(cols, dim=1).to(torch.bfloat16)
+    wp = torch.cat(cols, dim=1)
+    wp = round_tf32(wp.float()) if tf32 else wp.to(torch.bfloat16)
     if npad > cout:
         wp = torch.cat([wp, torch.zeros(npad - cout, wp.shape[1], dtype=wp.dtype, device=wp.device)], 0)
     return wp.contiguous()
@@ -61,9 +69,11 @@ def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None, al
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+    tf32 = srcs[0][0].dtype == torch.float32          # fp32 activations + tf32-rounded fp32 weights
+    assert (wpacked.dtype == torch.float32) == tf32
     rc = L.fd_conv2d_igemm(arr, n, _lib.ptr(wpacked), ktot, _lib.ptr(bias), _lib.ptr(out),
                            int(out_f32), out.shape[3], npad, B, H, W, _lib.ptr(stats), max_ctas,
-                           int(CTA_PAIRS) | (2 if HALO_TILES else 0), _lib.stream_ptr())
+                           int(CTA_PAIRS) | (2 if HALO_TILES else 0) | (4 if tf32 else 0), _lib.stream_ptr())
     _lib.check(rc, "fd_conv2d_igemm")
     if PROFILE is not None:
         e1.record()
@@ -94,7 +104,8 @@ def _fill_srcs(srcs):
     B, H, W = srcs[0][0].shape[:3]
     for i, src in enumerate(srcs):
         t, c0, cc, taps = src[:4]
-        assert t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape[:3] == (B, H, W)
+        assert t.is_cuda and t.dtype == srcs[0][0].dtype and t.dtype in (torch.bfloat16, torch.float32)
+        assert t.is_contiguous() and t.shape[:3] == (B, H, W)
         arr[i].ptr = t.data_ptr()
         arr[i].C = t.shape[3]
         arr[i].c_begin = c0
@@ -162,8 +173,8 @@ def chan_stats(x, slabs, out=None):
     B, H, W, C = x.shape
     if out is None:
         out = torch.empty(B, slabs, C, 2, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().fd_chan_stats(_lib.ptr(x), B, H * W, C, _lib.ptr(out), slabs, _lib.stream_ptr()),
-               "fd_chan_stats")
+    fn = _lib.lib().fd_chan_stats_f32 if x.dtype == torch.float32 else _lib.lib().fd_chan_stats
+    _lib.check(fn(_lib.ptr(x), B, H * W, C, _lib.ptr(out), slabs, _lib.stream_ptr()), "fd_chan_stats")
     return out
 
 
@@ -196,6 +207,11 @@ def gn_act_resample(srcs, scale_shift, out, mode, out_raw=None):
     s2 = srcs[1] if len(srcs) > 1 else None
     B, H, W, C1 = s1.shape
     C2 = s2.shape[3] if s2 is not None else 0
+    if s1.dtype == torch.float32:
+        rc = _lib.lib().fd_gn_act_resample_f32(_lib.ptr(s1), C1, _lib.ptr(s2), C2, _lib.ptr(scale_shift),
+                                               _lib.ptr(out), _lib.ptr(out_raw), B, H, W, mode, _lib.stream_ptr())
+        _lib.check(rc, "fd_gn_act_resample_f32")
+        return out
     if mode == 1 and (H % 4 or W % 4):
         rc = _lib.lib().fd_gn_act_down_any(_lib.ptr(s1), C1, _lib.ptr(s2), C2, _lib.ptr(scale_shift), _lib.ptr(out),
                                            _lib.ptr(out_raw), B, H, W, _lib.stream_ptr())
@@ -249,6 +265,11 @@ def pyramid_gather(part, bias4, lo, out):
 
 def conv_in(x4, w, b, out):
     B, H, W, _ = x4.shape
+    if out.dtype == torch.float32:
+        assert out.shape[3] == 64, "fp32 activations: the 4 -> 64 input conv of the FlowDec configuration"
+        _lib.check(_lib.lib().fd_conv_in_f32(_lib.ptr(x4), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), B, H, W,
+                                             _lib.stream_ptr()), "fd_conv_in_f32")
+        return out
     if out.shape[3] != 64:
         _lib.check(_lib.lib().fd_conv_in_any(_lib.ptr(x4), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), B, H, W,
                                              out.shape[3], _lib.stream_ptr()), "fd_conv_in_any")
@@ -260,8 +281,9 @@ def conv_in(x4, w, b, out):
 
 def combine(pyr4, w, b, h, out):
     B, H, W, C = h.shape
-    _lib.check(_lib.lib().fd_combine(_lib.ptr(pyr4), _lib.ptr(w), _lib.ptr(b), _lib.ptr(h), _lib.ptr(out),
-                                     ctypes.c_size_t(B * H * W), C, _lib.stream_ptr()), "fd_combine")
+    fn = _lib.lib().fd_combine_f32 if h.dtype == torch.float32 else _lib.lib().fd_combine
+    _lib.check(fn(_lib.ptr(pyr4), _lib.ptr(w), _lib.ptr(b), _lib.ptr(h), _lib.ptr(out),
+                  ctypes.c_size_t(B * H * W), C, _lib.stream_ptr()), "fd_combine")
     return out
 
 

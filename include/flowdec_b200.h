@@ -193,6 +193,21 @@ int fd_upfirdn2d_f32(const float* input, int planes, int in_h, int in_w, const f
                      int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                      float* out, fd_stream_t stream);
 
+/* ---- tf32 "precise" mode of the backbone ------------------------------------------------------------
+ * fd_conv2d_igemm with flags bit 2 (value 4): sources, weights and output are fp32 (weights rounded to tf32 at
+ * pack time), MMAs are kind::tf32 with fp32 accumulation — the precision class of the reference's own GPU convs
+ * (cuDNN with allow_tf32, layers.py:110-134).  Needs the halo tiles (flags 7): c_count % 32 == 0, W % 8 == 0,
+ * H % 16 == 0, even tile count; out_is_f32 = 1 with cout == npad in {128,256}, or the 4-channel pyramid form
+ * (npad 16, cout 4) which also exists for bf16 sources.  The `_f32` entry points below are the same kernels as
+ * their namesakes on fp32 NHWC activations. */
+int fd_chan_stats_f32(const void* x_f32, int B, int HW, int C, float* partial, int S, fd_stream_t stream);
+int fd_gn_act_resample_f32(const void* src1, int C1, const void* src2, int C2, const float* scale_shift,
+                           void* out, void* out_raw, int B, int H, int W, int mode, fd_stream_t stream);
+int fd_conv_in_f32(const void* in4, const float* w, const float* bias, void* out, int B, int H, int W,
+                   fd_stream_t stream);
+int fd_combine_f32(const void* pyr4, const float* w, const float* bias, const void* h, void* out, size_t npix, int C,
+                   fd_stream_t stream);
+
 /* ---- shape-generic kernels (7-level / bottleneck-attention NCSN++) ------------------
  * fd_conv2d_direct: same contract and packed weights as fd_conv2d_igemm, for shapes the tcgen05 tiles do not
  * take: any H, W; segment channel counts multiples of 8; cout rows of wpacked; out bf16 or fp32 NHWC with
