@@ -71,6 +71,10 @@ SIGNATURES = {
     "fd_gn_act_resample_f32": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "fd_conv_in_f32": [_P, _P, _P, _P, _I, _I, _I, _P],
     "fd_combine_f32": [_P, _P, _P, _P, _P, _Z, _I, _P],
+    "fd_dac_conv_tc": [_P, _I, _I, ctypes.c_longlong, _I, _P, _I, _I, ctypes.POINTER(ctypes.c_int), _P, _P,
+                       ctypes.c_longlong, _P, _I, _P, _P, _I, ctypes.c_longlong, _P],
+    "fd_dac_final_conv": [_P, ctypes.c_longlong, _P, _P, _P, _I, _I, _I, _P],
+    "fd_dac_nct_to_ntc": [_P, _P, _I, _I, _I, _P],
     "fd_upfirdn2d_f32": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "fd_conv2d_direct": [ctypes.POINTER(ConvSrc), _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "fd_attention": [_P, _I, _I, _I, _F, _P, _P],

@@ -14,8 +14,15 @@ hyper-parameter (decoder_dim, decoder_rates, n_codebooks, codebook_size, codeboo
 latent_dim / encoder_dim + encoder_rates, sample_rate) comes from that metadata.  Weight-norm
 (`weight_g`, `weight_v`) is folded and the codebooks are L2-normalised once at load.
 
-All arithmetic of encode / from_codes / decode runs in csrc/fd_dac.cu; there is no fallback.
+All arithmetic of encode / from_codes / decode runs in csrc/fd_dac.cu / csrc/fd_dac_tc.cu; there is no fallback.
+
+Decoder precision (`DAC.precision`): "tf32" (default when every channel count is a multiple of 32, as in the
+NDAC checkpoints: 1024 / 1536 / 768 / 384 / 192 / 96) runs each layer as a tcgen05 implicit GEMM on fp32
+time-major activations with tf32 operands and fp32 accumulation (residual adds in fp32); "fp32" runs the
+register-tiled CUDA-core kernels (bit-for-bit fp32 FMAs, ~50x slower).  Stated tolerance of the tf32 decoder:
+waveform rel-L2 <= 5e-3 vs the fp64 oracle (tests/test_dac_gpu.py prints the measured value).
 """
+import ctypes
 import math
 
 import numpy as np
@@ -165,6 +172,14 @@ class DAC(nn.Module):
             w, b = conv(f"{e}{n + 2}")
             self._enc_ops.append(("conv", w, b, a, 1, 1, False, False))
         self.quantizer = _Quantizer(self)
+        chans = [self.latent_dim] + [self.decoder_dim // 2 ** i for i in range(len(self.decoder_rates) + 1)]
+        self.tc_eligible = all(c % 32 == 0 for c in chans)
+        self.precision = "tf32" if self.tc_eligible else "fp32"
+        self._tc = None       # packed tf32 weights of the tensor-core decoder (built lazily on the device)
+
+    def _apply(self, fn, *a, **k):
+        self._tc = None
+        return super()._apply(fn, *a, **k)
 
     @property
     def device(self):
@@ -243,11 +258,113 @@ class DAC(nn.Module):
                 x = self._conv(y, w2, b2, a2, 1, 0, res=x)
         return x
 
+    # --------------------------------------------------------------------------------------- tensor-core decoder
+    def _tc_prepare(self):
+        """tf32-rounded GEMM weights of every decoder layer (see fd_dac_conv_tc in include/flowdec_b200.h)"""
+        if self._tc is not None:
+            return self._tc
+        from .ops import round_tf32
+        L = []
+
+        def conv_w(w):            # [Cout, Cin, K] -> [Cout, K*Cin]
+            return round_tf32(w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous())
+
+        def convtr_w(w, s):       # [Cin, Cout, 2s] -> [s*Cout, 2*Cin]: row r*Cout+co, col tap*Cin+ci = w[ci,co,r+tap*s]
+            cin, cout, _ = w.shape
+            return round_tf32(w.reshape(cin, cout, 2, s).permute(3, 1, 2, 0).reshape(s * cout, 2 * cin).contiguous())
+
+        for op in self._ops:
+            if op[0] == "conv":
+                _, w, b, a, dil, pad, _, tanh = op
+                w, b, a = self._t(w), self._t(b), self._t(a)
+                if tanh:
+                    L.append(("final", w.reshape(w.shape[1], w.shape[2]).contiguous(), b, a))
+                else:
+                    L.append(("conv", conv_w(w), b, [(j - 3) * dil for j in range(w.shape[2])]))
+            elif op[0] == "convtr":
+                _, w, b, a, s, pad = op
+                w, b, a = self._t(w), self._t(b), self._t(a)
+                L.append(("convtr", convtr_w(w, s), b.repeat(s).contiguous(), a, s, pad, w.shape[1]))
+            else:
+                _, (w1, b1, a1, d), (w2, b2, a2) = op
+                w1, b1, a1, w2, b2, a2 = (self._t(t) for t in (w1, b1, a1, w2, b2, a2))
+                L.append(("res", conv_w(w1), b1, a1, [(j - 3) * d for j in range(7)], conv_w(w2), b2, a2))
+        self._tc = L
+        return L
+
+    @staticmethod
+    def _tc_conv(x, Tin, x_bs, Cin, wp, offs, bias, residual, res_bs, alpha, alpha_mod, want_raw, want_act, Tout):
+        """one fd_dac_conv_tc launch; x / residual are (tensor, element offset) views with batch stride *_bs"""
+        xt, xo = x
+        B = xt.shape[0]
+        Ntot = wp.shape[0]
+        dev = xt.device
+        raw = torch.empty(B, Tout, Ntot, device=dev, dtype=torch.float32) if want_raw else None
+        act = torch.empty(B, Tout, Ntot, device=dev, dtype=torch.float32) if want_act else None
+        offs_c = (ctypes.c_int * len(offs))(*offs)
+        rp = ctypes.c_void_p(residual[0].data_ptr() + 4 * residual[1]) if residual is not None else ctypes.c_void_p(0)
+        rc = _lib.lib().fd_dac_conv_tc(ctypes.c_void_p(xt.data_ptr() + 4 * xo), B, Tin, x_bs, Cin, _lib.ptr(wp), Ntot,
+                                       len(offs), offs_c, _lib.ptr(bias), rp, res_bs, _lib.ptr(alpha), alpha_mod,
+                                       _lib.ptr(raw), _lib.ptr(act), Tout, Tout * Ntot, _lib.stream_ptr())
+        _lib.check(rc, "fd_dac_conv_tc")
+        return raw, act
+
+    def _decode_tc(self, z):
+        """the decoder as a chain of tf32 implicit GEMMs on time-major activations; every epilogue applies the NEXT
+        layer's Snake, so each layer reads an already activated tensor"""
+        L = self._tc_prepare()
+        B, D, T = z.shape
+        dev = z.device
+        zt = torch.empty(B, T, D, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib().fd_dac_nct_to_ntc(_lib.ptr(z), _lib.ptr(zt), B, D, T, _lib.stream_ptr()), "fd_dac_nct_to_ntc")
+
+        def next_alpha(i):
+            """Snake alpha applied to the output of layer i = the first activation of layer i + 1"""
+            nxt = L[i + 1]
+            return nxt[3] if nxt[0] in ("convtr", "res", "final") else None
+
+        assert L[0][0] == "conv" and L[-1][0] == "final"
+        _, wp, b, offs = L[0]
+        a = next_alpha(0)
+        _, act = self._tc_conv((zt, 0), T, T * D, D, wp, offs, b, None, 0, a, a.numel(), False, True, T)
+        cur_act, cur_raw = (act, 0), None          # (tensor, element offset) views
+        Tcur, C, bs = T, wp.shape[0], T * wp.shape[0]
+        for i in range(1, len(L) - 1):
+            lay = L[i]
+            a = next_alpha(i)
+            last_of_block = L[i + 1][0] != "res"
+            if lay[0] == "convtr":
+                _, wp, b, _, s, pad, cout = lay
+                raw, act = self._tc_conv(cur_act, Tcur, bs, C, wp, [0, -1], b, None, 0, a, cout, True, True, Tcur + 1)
+                Tout = (Tcur - 1) * s - 2 * pad + 2 * s
+                bs = (Tcur + 1) * s * cout
+                cur_raw, cur_act = (raw, pad * cout), (act, pad * cout)
+                Tcur, C = Tout, cout
+            else:
+                _, w1, b1, _, offs, w2, b2, a2 = lay
+                _, h = self._tc_conv(cur_act, Tcur, bs, C, w1, offs, b1, None, 0, a2, C, False, True, Tcur)
+                raw, act = self._tc_conv((h, 0), Tcur, Tcur * C, C, w2, [0], b2, cur_raw, bs, a, C,
+                                         not last_of_block, True, Tcur)
+                bs = Tcur * C
+                cur_raw, cur_act = ((raw, 0) if raw is not None else None), (act, 0)
+        _, wf, bf, _ = L[-1]
+        out = torch.empty(B, 1, Tcur, device=dev, dtype=torch.float32)
+        xt, xo = cur_act
+        rc = _lib.lib().fd_dac_final_conv(ctypes.c_void_p(xt.data_ptr() + 4 * xo), bs, _lib.ptr(wf), _lib.ptr(bf),
+                                          _lib.ptr(out), B, Tcur, C, _lib.stream_ptr())
+        _lib.check(rc, "fd_dac_final_conv")
+        return out
+
     @torch.no_grad()
     def decode(self, z):
         """z [B, latent_dim, T] -> waveform [B, 1, ~T*hop] (dac.DAC.decode, demo.ipynb:105)"""
         self._require_cuda()
-        return self._run(self._ops, z.to(self.device, torch.float32).contiguous())
+        z = z.to(self.device, torch.float32).contiguous()
+        if self.precision == "tf32":
+            if not self.tc_eligible:
+                raise RuntimeError("precision 'tf32' needs decoder channel counts that are multiples of 32")
+            return self._decode_tc(z)
+        return self._run(self._ops, z)
 
     def preprocess(self, audio_data, sample_rate=None):
         """dac.DAC.preprocess (demo.ipynb:101): zero-pad on the right to a multiple of hop_length.

@@ -179,6 +179,27 @@ int fd_dac_conv_transpose1d(const float* x, const float* w, const float* bias, c
                             float* out, int B, int Cin, int Cout, int Tin, int stride, int pad,
                             fd_stream_t stream);
 
+/* ---- NDAC decoder on tensor cores (fd_dac_tc.cu): activations fp32 time-major [B, T, C] ------------------
+ * One decoder layer as a tf32 implicit GEMM: out[b,t,n] = bias[n] + sum_tap sum_c x[b, t + tap_offsets[tap], c] *
+ * wpacked[n, tap*Cin + c] (+ residual[b,t,n]); x rows outside [0, Tin) read as zero.  wpacked fp32 [Ntot, ntaps*Cin],
+ * tf32-rounded; Cin % 32 == 0, Ntot % 32 == 0, max - min of tap_offsets (HOST int array) <= 56.
+ *   Conv1d(k=7, dilation d, pad 3d): offsets (j-3)*d.  Conv1d(k=1): {0}.
+ *   ConvTranspose1d(k=2s, stride s, pad p): offsets {0,-1}, Ntot = s*Cout, wpacked[r*Cout+co, tap*Cin+ci] =
+ *   w[ci,co,r+tap*s], Tout_rows = Tin + 1; the result [B, Tin+1, s*Cout] read as [B, (Tin+1)*s, Cout] holds the
+ *   transposed conv's output at rows p .. p + Tout - 1.
+ * out_raw and/or out_act (either may be NULL): fp32 [B, Tout_rows, Ntot] with batch stride out_bstride (elements);
+ * out_act = Snake1d(out_raw) with alpha_next[n % alpha_mod] (x + sin^2(a x)/(a + 1e-9)), rounded to tf32 — the
+ * NEXT layer's activation applied in this layer's epilogue.  x / residual batch strides in elements. */
+int fd_dac_conv_tc(const float* x, int B, int Tin, long long x_bstride, int Cin, const float* wpacked, int Ntot,
+                   int ntaps, const int* tap_offsets, const float* bias, const float* residual, long long res_bstride,
+                   const float* alpha_next, int alpha_mod, float* out_raw, float* out_act, int Tout_rows,
+                   long long out_bstride, fd_stream_t stream);
+/* last decoder layer: out[b,t] = tanh(bias[0] + sum_{k<7,c} x_act[b, t+k-3, c] * w[c,k]);  w fp32 [C,7] */
+int fd_dac_final_conv(const float* x_act, long long x_bstride, const float* w, const float* bias, float* out, int B,
+                      int T, int C, fd_stream_t stream);
+/* [B,C,T] -> [B,T,C], values rounded to tf32 (the latent from fd_rvq_from_codes entering the tensor-core decoder) */
+int fd_dac_nct_to_ntc(const float* in, float* out, int B, int C, int T, fd_stream_t stream);
+
 /* ---- the reference's native op, as a C entry point ------------------------------------------------
  * upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1) of
  * flowdec/backbones/ncsnpp_utils/op/upfirdn2d.cpp:38-48 (kernel op/upfirdn2d_kernel.cu:118-218, semantics

@@ -185,3 +185,74 @@ def test_dac_preprocess_encode_decode():
     out = model(audio.cuda(), 48000, n_quantizers=4)
     assert out["audio"].shape == audio.shape and torch.equal(out["codes"], codes)
     assert rel(out["audio"], model.decode(zq)[..., :4001]) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core decoder (fd_dac_tc.cu): tf32 operands, fp32 accumulation, time-major activations
+def _tc_layer(x_ntc, w_packed, offs, bias, residual=None, alpha=None, alpha_mod=0, want_raw=True, Tout=None):
+    B, T, C = x_ntc.shape
+    raw, act = DAC._tc_conv((x_ntc, 0), T, T * C, C, w_packed, offs, bias, (residual, 0) if residual is not None else None,
+                            (residual.shape[1] * residual.shape[2]) if residual is not None else 0, alpha, alpha_mod,
+                            want_raw, alpha is not None, Tout or T)
+    return raw, act
+
+
+@pytest.mark.parametrize("C,Cout,dil,T", [(96, 96, 1, 300), (192, 192, 9, 257), (64, 384, 3, 130), (1024, 1536, 1, 75)])
+def test_tc_conv1d_layer(C, Cout, dil, T):
+    from flowdec_b200.ops import round_tf32
+    torch.manual_seed(0)
+    B = 2
+    x = torch.randn(B, C, T)
+    w = torch.randn(Cout, C, 7) / math.sqrt(7 * C)
+    b = torch.randn(Cout) * 0.1
+    alpha = torch.rand(Cout) + 0.5
+    res = torch.randn(B, Cout, T)
+    ref_raw = F.conv1d(x.double(), w.double(), b.double(), dilation=dil, padding=3 * dil) + res.double()
+    ref_act = D.snake(ref_raw, alpha.double().reshape(1, -1, 1))
+    wp = round_tf32(w.permute(0, 2, 1).reshape(Cout, -1).contiguous()).cuda()
+    raw, act = _tc_layer(x.permute(0, 2, 1).contiguous().cuda(), wp, [(j - 3) * dil for j in range(7)], b.cuda(),
+                         residual=res.permute(0, 2, 1).contiguous().cuda(), alpha=alpha.cuda(), alpha_mod=Cout)
+    r1, r2 = rel(raw.cpu().permute(0, 2, 1), ref_raw), rel(act.cpu().permute(0, 2, 1), ref_act)
+    print(f"\ntc conv1d C={C}->{Cout} dil={dil}: rel-L2 raw {r1:.3e} act {r2:.3e}")
+    assert r1 < 1.5e-3 and r2 < 1.5e-3
+
+
+@pytest.mark.parametrize("Cin,Cout,s,T", [(128, 64, 2, 100), (256, 128, 4, 150), (192, 96, 5, 40), (1536, 768, 8, 33)])
+def test_tc_conv_transpose_layer(Cin, Cout, s, T):
+    from flowdec_b200.ops import round_tf32
+    torch.manual_seed(1)
+    B = 2
+    x = torch.randn(B, Cin, T)
+    w = torch.randn(Cin, Cout, 2 * s) / math.sqrt(Cin * 2)
+    b = torch.randn(Cout) * 0.1
+    pad = math.ceil(s / 2)
+    ref = F.conv_transpose1d(x.double(), w.double(), b.double(), stride=s, padding=pad)
+    wp = round_tf32(w.reshape(Cin, Cout, 2, s).permute(3, 1, 2, 0).reshape(s * Cout, 2 * Cin).contiguous()).cuda()
+    raw, _ = _tc_layer(x.permute(0, 2, 1).contiguous().cuda(), wp, [0, -1], b.repeat(s).cuda(), Tout=T + 1)
+    Tout = ref.shape[-1]
+    got = raw.cpu().reshape(B, (T + 1) * s, Cout)[:, pad:pad + Tout].permute(0, 2, 1)
+    r = rel(got, ref)
+    print(f"\ntc conv_transpose1d {Cin}->{Cout} s={s}: rel-L2 {r:.3e}")
+    assert r < 1.5e-3
+
+
+@pytest.mark.parametrize("latent,dim,rates,nq,T", [(64, 256, (4, 2), 3, 37), (128, 512, (8, 5, 2), 6, 150)])
+def test_tc_decode_end_to_end(latent, dim, rates, nq, T):
+    """whole decoder on tensor cores vs the fp64 oracle; the fp32 CUDA-core decoder on the same model is the A/B"""
+    sd = D.synth_dac_state_dict(latent, dim, rates, nq, seed=2)
+    model = DAC(sd, decoder_dim=dim, decoder_rates=rates, n_codebooks=nq, latent_dim=latent, sample_rate=48000)
+    assert model.tc_eligible and model.precision == "tf32"
+    model = model.to("cuda").eval()
+    assert all(t.is_cuda for t in model.op_tensors().values())
+    codes = torch.randint(0, 1024, (3, nq, T), generator=torch.Generator().manual_seed(3))
+    sd64 = {k: v.double() for k, v in sd.items()}
+    with torch.no_grad():
+        x64 = D.decode(sd64, D.from_codes(sd64, codes), rates)
+    zq, _, _ = model.quantizer.from_codes(codes)
+    x_tc = model.decode(zq)
+    model.precision = "fp32"
+    x_32 = model.decode(zq)
+    assert x_tc.shape == x64.shape == x_32.shape
+    r_tc, r_32 = rel(x_tc.cpu(), x64), rel(x_32.cpu(), x64)
+    print(f"\nNDAC decode rel-L2 vs fp64 oracle: tensor-core tf32 {r_tc:.3e}, CUDA-core fp32 {r_32:.3e}")
+    assert r_tc <= 5e-3 and r_32 <= 1e-3
