@@ -189,6 +189,12 @@ def test_dac_preprocess_encode_decode():
 
 # ------------------------------------------------------------------------------------------------
 # tensor-core decoder (fd_dac_tc.cu): tf32 operands, fp32 accumulation, time-major activations
+def _rt(x):
+    """fp64 tensor with values rounded to tf32 (10-bit mantissa)"""
+    i = x.float().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32).double()
+
+
 def _tc_layer(x_ntc, w_packed, offs, bias, residual=None, alpha=None, alpha_mod=0, want_raw=True, Tout=None):
     B, T, C = x_ntc.shape
     raw, act = DAC._tc_conv((x_ntc, 0), T, T * C, C, w_packed, offs, bias, (residual, 0) if residual is not None else None,
@@ -248,11 +254,21 @@ def test_tc_decode_end_to_end(latent, dim, rates, nq, T):
     sd64 = {k: v.double() for k, v in sd.items()}
     with torch.no_grad():
         x64 = D.decode(sd64, D.from_codes(sd64, codes), rates)
+        # the tf32 floor of THIS (synthetic, error-amplifying) decoder: the fp64 oracle with only the conv operands
+        # rounded to tf32 — what any tf32 execution (incl. the reference's cuDNN default) would show
+        c1, ct = F.conv1d, F.conv_transpose1d
+        try:
+            F.conv1d = lambda x, w, b=None, **k: c1(_rt(x), _rt(w), b, **k)
+            F.conv_transpose1d = lambda x, w, b=None, **k: ct(_rt(x), _rt(w), b, **k)
+            x_em = D.decode(sd64, D.from_codes(sd64, codes), rates)
+        finally:
+            F.conv1d, F.conv_transpose1d = c1, ct
     zq, _, _ = model.quantizer.from_codes(codes)
     x_tc = model.decode(zq)
     model.precision = "fp32"
     x_32 = model.decode(zq)
     assert x_tc.shape == x64.shape == x_32.shape
-    r_tc, r_32 = rel(x_tc.cpu(), x64), rel(x_32.cpu(), x64)
-    print(f"\nNDAC decode rel-L2 vs fp64 oracle: tensor-core tf32 {r_tc:.3e}, CUDA-core fp32 {r_32:.3e}")
-    assert r_tc <= 5e-3 and r_32 <= 1e-3
+    r_tc, r_32, r_em = rel(x_tc.cpu(), x64), rel(x_32.cpu(), x64), rel(x_em, x64)
+    print(f"\nNDAC decode rel-L2 vs fp64 oracle: tensor-core tf32 {r_tc:.3e} (tf32-operand emulation of the oracle "
+          f"{r_em:.3e}), CUDA-core fp32 {r_32:.3e}")
+    assert r_tc <= 2.0 * r_em + 1e-4 and r_32 <= 1e-3
