@@ -393,7 +393,8 @@ class NCSNpp(nn.Module):
                     b16 = torch.zeros(16, device=dev)
                     b16[:m.bias.shape[0]] = m.bias.float()
                     P[i] = dict(w=self._pack([(m.weight.float(), 9)], 16), b=b16,
-                                wt=ops.pack_tap_weight(m.weight.float()), b4=m.bias.float().contiguous())
+                                wt=ops.pack_tap_weight(m.weight.float(), tf32=self.precision == "tf32"),
+                                b4=m.bias.float().contiguous())
             P["conv_in_w"] = self.all_modules[3].weight.float().contiguous()
             P["conv_in_b"] = self.all_modules[3].bias.float().contiguous()
             P["Wf"] = self.all_modules[0].W.float().contiguous()
@@ -643,12 +644,14 @@ class NCSNpp(nn.Module):
             pc = P[idx]
             C = h.shape[3]
             ph = ws.get(f"pyr_out{lvl}", (B, H, W, 4), torch.float32, dev)
-            if self.pyramid_halo and ops.halo_eligible(B, H, W, 16) and C % 64 == 0:
-                # 3x3 conv C -> 4 on the halo kernel (N = 16): GroupNorm+SiLU in the operand transform, one read of
-                # h, fp32 float4 per pixel out; nothing is materialised
+            if self.pyramid_halo and ops.halo_eligible(B, H, W, 48) and C % 64 == 0:
+                # "GEMM first, shift after" on the halo kernel (N = 48, 1 tap): GroupNorm+SiLU in the operand
+                # transform (nothing is materialised), 36 per-tap products per pixel out, then the gather-sum
                 ss = self._gn_scale_shift([h], g["g"], g["b"], scache, "gn_ss")
-                ops.conv_igemm([(h, 0, C, 9, ss, 0)], pc["w"], pc["b"], ph, self.max_ctas)
-                pyramid = ph if pyramid is None else ops.pyramid_up_add(pyramid, ph, ph)
+                part = ws.get("pyr_part", (B, H, W, 36), torch.float32, dev)
+                ops.conv_igemm([(h, 0, C, 1, ss, 0)], pc["wt"], None, part, self.max_ctas, algo_k=9 * C, algo_cout=4)
+                ops.pyramid_gather(part, pc["b4"], pyramid, ph)
+                pyramid = ph
             elif self.pyramid_shift_after_gemm and ops.tensor_conv_ok(B, H, W, 48, [C], out_f32=True):
                 # one pass over `a`: 36 per-tap products per pixel on tensor cores, then a gather-sum
                 a = self._gn_act([h], g["g"], g["b"], 0, scache, "act")

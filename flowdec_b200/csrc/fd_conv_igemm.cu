@@ -486,10 +486,12 @@ struct HaloParams {
 
 // TF32: fp32 activations / weights in HBM and shared memory, kind::tf32 MMAs (K = 8 per instruction, 32 channels
 // per 128-byte k-slice: the byte geometry of boxes, swizzle and descriptors is identical to bf16), fp32 output.
-// OUT4: N = 16 accumulator columns of which 4 are real — the pyramid convs C -> 4 (ncsnpp.py:218,230) — written
-// by the epilogue as one float4 per pixel.
-template <int N, bool TF32, bool OUT4>
+// OUTC (4 or 36): fp32 pixel-major output [B,H,W,OUTC] written directly by the epilogue — the pyramid convs C -> 4
+// (ncsnpp.py:218,230), either as a 3x3 conv with N = 16 (4 real columns) or, much cheaper on the tensor pipe, as the
+// 1-tap "GEMM first" form with N = 48 (36 = 9 taps x 4 outputs, summed over shifted pixels by fd_pyramid_gather).
+template <int N, bool TF32, int OUTC>
 struct HaloCfg {
+  static constexpr bool OUT4 = OUTC != 0;      // fp32 pixel-major output of OUTC channels (no TMA store, no statistics)
   static constexpr int kStagesA = 3;
   static constexpr int kStagesB = 6;
   static constexpr int kSliceC = TF32 ? 32 : 64;          // channels per k-slice (128 bytes)
@@ -501,7 +503,7 @@ struct HaloCfg {
   static constexpr int kSmemBytes = 1024 + kStagesA * kHaloStageBytes + kStagesB * kBBytes + kOutBytes + N * 4 +
                                     kSsFloats * 4 + 512 + kStatScratch;
   static_assert(kBBytes % 1024 == 0, "B stage must keep the 1024-byte swizzle alignment");
-  static_assert(!OUT4 || N == 16, "OUT4 is the N = 16 pyramid tile");
+  static_assert(OUTC == 0 || (OUTC == 4 && N == 16) || (OUTC == 36 && N == 48), "fp32 pixel-major forms: 4 of 16 or 36 of 48 columns");
 };
 
 // Transform-warp placement.  FD_XF_LAYOUT 0 (default): warps 7..14 (two of them share the MMA warp's scheduler
@@ -513,9 +515,10 @@ struct HaloCfg {
 #endif
 constexpr int kHaloXfThreads = FD_XF_LAYOUT ? 544 : 480;
 
-template <int N, bool XF, bool TF32, bool OUT4>
+template <int N, bool XF, bool TF32, int OUTC>
 __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
-  using Cfg = HaloCfg<N, TF32, OUT4>;
+  using Cfg = HaloCfg<N, TF32, OUTC>;
+  constexpr bool OUT4 = OUTC != 0;
   constexpr int SA = Cfg::kStagesA, SB = Cfg::kStagesB, B_BYTES = Cfg::kBBytes;
   constexpr int kSliceC = Cfg::kSliceC;
   extern __shared__ uint8_t smem_raw[];
@@ -715,19 +718,32 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * N);
       if constexpr (OUT4) {
-        // pyramid conv C -> 4: columns 0..3 of the 16-column accumulator, one float4 per pixel
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_row, v);
-        tmem_ld_wait();
-        tc_fence_before_sync();
-        mbar_arrive_remote(&tempty_bar[acc], 0);
+        // pixel-major fp32 output: the first OUTC accumulator columns of this pixel's row
         const int hl = row >> 3, wl = row & 7;
-        float4 r;
-        r.x = __uint_as_float(v[0]) + sBias[0];
-        r.y = __uint_as_float(v[1]) + sBias[1];
-        r.z = __uint_as_float(v[2]) + sBias[2];
-        r.w = __uint_as_float(v[3]) + sBias[3];
-        *reinterpret_cast<float4*>(p.out4 + ((static_cast<size_t>(n) * p.H + (h0 + hl)) * p.W + (w0 + wl)) * 4) = r;
+        float* o = p.out4 + ((static_cast<size_t>(n) * p.H + (h0 + hl)) * p.W + (w0 + wl)) * OUTC;
+        constexpr int kGroups = (OUTC + 15) / 16;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_row + g * 16, v);
+          tmem_ld_wait();
+          if (g == kGroups - 1) {
+            tc_fence_before_sync();
+            mbar_arrive_remote(&tempty_bar[acc], 0);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = g * 16 + q * 4;
+            if (c < OUTC) {
+              float4 r;
+              r.x = __uint_as_float(v[q * 4 + 0]) + sBias[c + 0];
+              r.y = __uint_as_float(v[q * 4 + 1]) + sBias[c + 1];
+              r.z = __uint_as_float(v[q * 4 + 2]) + sBias[c + 2];
+              r.w = __uint_as_float(v[q * 4 + 3]) + sBias[c + 3];
+              *reinterpret_cast<float4*>(o + c) = r;
+            }
+          }
+        }
       } else if constexpr (TF32) {
         constexpr int kChunks = N / 32;           // 32 fp32 channels = one 128-byte staging row
         const int slab = rem * 4 + ew;
@@ -1036,10 +1052,10 @@ static int launch_conv(const ConvParams& p, int max_ctas, cudaStream_t stream) {
   return check_launch("fd_conv2d_igemm");
 }
 
-template <int N, bool XF, bool TF32 = false, bool OUT4 = false>
+template <int N, bool XF, bool TF32 = false, int OUTC = 0>
 static int launch_halo(const HaloParams& p, int max_ctas, cudaStream_t stream) {
-  auto kern = conv_halo_kernel<N, XF, TF32, OUT4>;
-  using Cfg = HaloCfg<N, TF32, OUT4>;
+  auto kern = conv_halo_kernel<N, XF, TF32, OUTC>;
+  using Cfg = HaloCfg<N, TF32, OUTC>;
   static bool attr_set[kMaxDevices] = {false};   // function attributes are per device
   const int dev = current_device();
   if (!attr_set[dev]) {
@@ -1111,9 +1127,10 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
     // "halo" kernel: 16x8 tiles, one A box per k-slice for all nine taps, optional fused GN+SiLU, optional tf32,
     // optional 4-channel fp32 output (pyramid convs)
     const bool out4 = out_is_f32 && npad == 16 && cout == 4;
+    const bool out36 = out_is_f32 && npad == 48 && cout == 36;   // "GEMM first" pyramid form (1-tap sources)
     const bool geom_ok = (flags & 1) && (flags & 2) && (W % kHaloTileW == 0) && (H % kHaloTileH == 0) &&
                          ((static_cast<long long>(B) * (H / kHaloTileH) * (W / kHaloTileW)) % 2 == 0);
-    const bool halo_ok = geom_ok && (out4 || ((npad == 128 || npad == 256) && (out_is_f32 != 0) == tf32));
+    const bool halo_ok = geom_ok && (out4 || out36 || ((npad == 128 || npad == 256) && (out_is_f32 != 0) == tf32));
     FD_REQUIRE(halo_ok || !any_xf, "fd_conv2d_igemm: fused GroupNorm+SiLU needs the halo kernel "
                "(flags 3, W %% 8 == 0, H %% 16 == 0, even tile count)");
     FD_REQUIRE(halo_ok || !tf32, "fd_conv2d_igemm: tf32 (flags bit 2) needs the halo kernel "
@@ -1139,7 +1156,7 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
       }
       FD_REQUIRE(ssoff <= 512, "fd_conv2d_igemm: at most 512 transformed channels (got %d)", ssoff);
       if (make_weight_map(&hp.b_map, wpacked, npad, ktot, npad / 2, tf32)) return 1;
-      if (!out4) {
+      if (!out4 && !out36) {
         FD_REQUIRE(cout == npad, "fd_conv2d_igemm: NHWC output needs cout == npad");
         if (make_nhwc_map(&hp.out_map, out, B, H, W, cout, 0, cout, kHaloTileH, kHaloTileW, tf32)) return 1;
       } else {
@@ -1161,10 +1178,16 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
         hp.xf_mode = m ? atoi(m) : 0;
       }
       if (out4) {
-        if (tf32) return any_xf ? launch_halo<16, true, true, true>(hp, max_ctas, stream)
-                                : launch_halo<16, false, true, true>(hp, max_ctas, stream);
-        return any_xf ? launch_halo<16, true, false, true>(hp, max_ctas, stream)
-                      : launch_halo<16, false, false, true>(hp, max_ctas, stream);
+        if (tf32) return any_xf ? launch_halo<16, true, true, 4>(hp, max_ctas, stream)
+                                : launch_halo<16, false, true, 4>(hp, max_ctas, stream);
+        return any_xf ? launch_halo<16, true, false, 4>(hp, max_ctas, stream)
+                      : launch_halo<16, false, false, 4>(hp, max_ctas, stream);
+      }
+      if (out36) {
+        if (tf32) return any_xf ? launch_halo<48, true, true, 36>(hp, max_ctas, stream)
+                                : launch_halo<48, false, true, 36>(hp, max_ctas, stream);
+        return any_xf ? launch_halo<48, true, false, 36>(hp, max_ctas, stream)
+                      : launch_halo<48, false, false, 36>(hp, max_ctas, stream);
       }
       if (tf32) {
         if (npad == 256) return any_xf ? launch_halo<256, true, true>(hp, max_ctas, stream)

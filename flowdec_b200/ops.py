@@ -18,7 +18,7 @@ HALO_TILES = True
 
 def halo_eligible(B, H, W, npad):
     """mirror of the dispatch rule in fd_conv2d_igemm (npad 16 = the 4-channel fp32 pyramid form)"""
-    return (CTA_PAIRS and HALO_TILES and npad in (16, 128, 256) and W % 8 == 0 and H % 16 == 0
+    return (CTA_PAIRS and HALO_TILES and npad in (16, 48, 128, 256) and W % 8 == 0 and H % 16 == 0
             and (B * (H // 16) * (W // 8)) % 2 == 0)
 
 
@@ -248,10 +248,11 @@ def pyramid_up_add(lo, add, out):
     return out
 
 
-def pack_tap_weight(w, npad=48):
-    """[Cout(4), Cin, 3, 3] -> bf16 [npad, Cin]: row tap*4+co = w[co, :, kh, kw] (tap = kh*3+kw)"""
+def pack_tap_weight(w, npad=48, tf32=False):
+    """[Cout(4), Cin, 3, 3] -> bf16 (or tf32-rounded fp32) [npad, Cin]: row tap*4+co = w[co, :, kh, kw] (tap = kh*3+kw)"""
     cout, cin = w.shape[:2]
-    wp = w.permute(2, 3, 0, 1).reshape(9 * cout, cin).to(torch.bfloat16)
+    wp = w.permute(2, 3, 0, 1).reshape(9 * cout, cin)
+    wp = round_tf32(wp.float().contiguous()) if tf32 else wp.to(torch.bfloat16)
     pad = torch.zeros(npad - 9 * cout, cin, dtype=wp.dtype, device=wp.device)
     return torch.cat([wp, pad], 0).contiguous()
 

@@ -201,9 +201,12 @@ def test_config2_full_size_properties(model):
     eps = torch.randn(B, 1, 768, 256, dtype=torch.complex64, generator=g)
     out = model.enhance(y, N=3, solver="midpoint", noise=eps)
     assert out.shape == y.shape and torch.isfinite(out).all()
-    assert out[5].abs().max() < 10.0
-    for i in (0, 17, 31):
+    # (the all-zero clip is NOT silent after the untrained synthetic network: the CPU oracle gives max|x| = 460 for
+    #  this clip and noise draw; what must hold is finiteness and independence from its neighbours)
+    for i in (0, 5, 17, 31):
         one = model.enhance(y[i:i + 1], N=3, solver="midpoint", noise=eps[i:i + 1])
         assert torch.equal(one, out[i:i + 1]), f"clip {i} depends on its batch neighbours"
     half = model.enhance(0.5 * y, N=3, solver="midpoint", noise=eps)
-    assert torch.equal(half, 0.5 * out)
+    keep = [i for i in range(B) if i != 5]
+    assert torch.equal(half[keep], 0.5 * out[keep])
+    assert torch.equal(half[5], out[5])          # the all-zero clip is normalised by 1 either way (util/other.py:77)

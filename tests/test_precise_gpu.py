@@ -157,3 +157,29 @@ def test_precise_enhance_vs_golden(model, N, solver, key, file):
     print(f"\nenhance {solver} N={N}: SNR vs reference golden tf32 {s32:.2f} dB, bf16 {s16:.2f} dB")
     assert torch.equal(x32, x32b)
     assert s32 >= 50.0 and s16 >= 30.0 and s32 >= s16 + 10.0
+
+
+@pytest.mark.parametrize("tf32", [False, True])
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 128), (1, 96, 32, 256)])
+def test_conv_out36_gemm_first_pyramid_form(B, H, W, C, tf32):
+    """the production pyramid path: 1-tap halo GEMM with N = 48 (36 per-tap products per pixel, GroupNorm+SiLU fused
+    into the operand) followed by fd_pyramid_gather (shifted sum + bias + FIR-up of the coarser pyramid)"""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, H, W, C, generator=g) * 1.5 - 0.2
+    if not tf32:
+        x = x.to(torch.bfloat16)
+    w = torch.randn(4, C, 3, 3, generator=g) / math.sqrt(9 * C)
+    bias = torch.randn(4, generator=g) * 0.1
+    lo = torch.randn(B, H // 2, W // 2, 4, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    ss, act = _gn_ss([x.float()], gamma, beta)
+    from oracle import flowdec_oracle as O
+    ref = F.conv2d(act, w.double(), bias.double(), padding=1) + O.fir_up2(lo.permute(0, 3, 1, 2)).double()
+    wt = ops.pack_tap_weight(w, tf32=tf32).cuda()
+    part = torch.empty(B, H, W, 36, device="cuda", dtype=torch.float32)
+    ops.conv_igemm([(x.cuda(), 0, C, 1, ss.cuda(), 0)], wt, None, part)
+    out = ops.pyramid_gather(part, bias.cuda(), lo.cuda(), torch.empty(B, H, W, 4, device="cuda"))
+    torch.cuda.synchronize()
+    r = rel_l2(out.cpu().permute(0, 3, 1, 2), ref)
+    print(f"\nout36 + gather C={C} tf32={tf32}: rel-L2 {r:.3e}")
+    assert r <= (1.5e-3 if tf32 else 8e-3)
