@@ -220,7 +220,10 @@ class NCSNpp(nn.Module):
         self.stats_slabs = 64
         self.fuse_stats = True     # GroupNorm partial sums produced by the conv epilogue
         self.pyramid_shift_after_gemm = True
-        self.pyramid_halo = True        # pyramid convs on the N = 16 halo kernel with the fused transform
+        # pyramid convs on the halo kernel (1-tap N = 48 form with the fused transform): measured SLOWER than the
+        # materialised pass + per-tap GEMM (r2b: 1.52 + 0.23 ms vs 0.75 + 0.45 + 0.23 ms per forward of 8 clips) because the
+        # exposed transform chain, not the tensor pipe, paces a kernel with so few MMAs; used by the tf32 mode only
+        self.pyramid_halo = False
         self.fuse_gn_into_conv = True   # GroupNorm+SiLU applied inside the conv kernel (needs ops.HALO_TILES)
         self.max_ctas = 0
         self.precision = "bf16"
@@ -644,7 +647,7 @@ class NCSNpp(nn.Module):
             pc = P[idx]
             C = h.shape[3]
             ph = ws.get(f"pyr_out{lvl}", (B, H, W, 4), torch.float32, dev)
-            if self.pyramid_halo and ops.halo_eligible(B, H, W, 48) and C % 64 == 0:
+            if (self.pyramid_halo or self.precision == "tf32") and ops.halo_eligible(B, H, W, 48) and C % 64 == 0:
                 # "GEMM first, shift after" on the halo kernel (N = 48, 1 tap): GroupNorm+SiLU in the operand
                 # transform (nothing is materialised), 36 per-tap products per pixel out, then the gather-sum
                 ss = self._gn_scale_shift([h], g["g"], g["b"], scache, "gn_ss")
