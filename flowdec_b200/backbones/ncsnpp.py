@@ -516,13 +516,11 @@ class NCSNpp(nn.Module):
                 (all(len(s) <= 4 or s[4] is None for s in srcs) or ops.halo_eligible(B, H, W, wp.shape[0])):
             st = None
             if self.fuse_stats and stats_name is not None:
-                S = ops.conv_stats_slabs(H, W)
-                # large S: shared scratch, compacted below into a per-tensor buffer; small S: kept as is
-                st = self._ws.get("conv_stats" if S > self.stats_slabs else stats_name, (B, S, cout, 2),
-                                  torch.float32, out.device)
+                # one slab per conv tile; fd_gn_finalize reduces them directly (no compaction pass)
+                st = self._ws.get(stats_name, (B, ops.conv_stats_slabs(H, W), cout, 2), torch.float32, out.device)
             ops.conv_igemm(srcs, wp, bias, out, self.max_ctas, algo_k=algo_k, stats=st)
             if st is not None:
-                scache[out.data_ptr()] = self._compact_stats(st, stats_name)
+                scache[out.data_ptr()] = st
         else:
             ops.conv_direct(srcs, wp, bias, out)
         return out

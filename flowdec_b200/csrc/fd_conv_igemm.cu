@@ -66,8 +66,9 @@ struct ConvCfg {
   static_assert(kBBytes % 1024 == 0, "B stage must keep the 1024-byte swizzle alignment");
   static constexpr int kOutBytes = (N >= 64) ? 2 * kTileM * 128 : 0;  // two 64-channel staging tiles
   static constexpr int kTmemCols = (2 * N <= 32) ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
+  static constexpr int kStatBytes = (N >= 64) ? 4 * 64 * 2 * 4 : 0;   // per-warp column sums of one chunk
   static constexpr int kSmemBytes =
-      1024 + kStages * (kABytes + kBBytes) + kOutBytes + N * 4 + 256;
+      1024 + kStages * (kABytes + kBBytes) + kOutBytes + N * 4 + 256 + kStatBytes;
 };
 
 // One 32-column half of an epilogue chunk for this lane's pixel row: + bias, bf16 pack into the
@@ -142,6 +143,19 @@ __device__ __forceinline__ void epilogue_half(const uint32_t (&v)[32], uint32_t 
     FD_BFLY(1, 1)
 #undef FD_BFLY
     *reinterpret_cast<float2*>(stat_dst + lane * 2) = make_float2(f[0], q[0]);
+  }
+}
+
+// GroupNorm partial sums, one slab per TILE: every epilogue warp leaves the (sum, sum of squares) of its 32 rows
+// for `cols` columns in shared memory (sStat[warp][col][2]); after the chunk's barrier the 128 epilogue threads add
+// the four warps in a fixed order ((w0 + w1) + (w2 + w3): deterministic, independent of the batch) and write
+// dst[col][2].  4x fewer statistics bytes than one slab per warp, and the consumer reduces them in one kernel.
+__device__ __forceinline__ void stats_combine_store(const float* sStat, int cols, int et, float* dst) {
+  if (et < 2 * cols) {
+    const int col = et >> 1, st = et & 1;
+    const float a = sStat[(0 * 64 + col) * 2 + st], b = sStat[(1 * 64 + col) * 2 + st];
+    const float c = sStat[(2 * 64 + col) * 2 + st], d = sStat[(3 * 64 + col) * 2 + st];
+    dst[col * 2 + st] = (a + b) + (c + d);
   }
 }
 
@@ -389,9 +403,10 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         }
       } else {
         constexpr int kChunks = N / 64;
-        const int slab = rem * 4 + ew;   // GroupNorm partial-sum slab of this warp's 32 pixels
-        float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * (tiles_per_img * 4) + slab) * N) * 2
-                                  : nullptr;
+        // GroupNorm partial-sum slab of this tile (the four warps' sums are combined through shared memory)
+        float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * tiles_per_img + rem) * N) * 2 : nullptr;
+        float* sStat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+        float* my_stat = sStat + ew * 128;
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ++ch) {
           uint32_t v0[32], v1[32];
@@ -408,10 +423,11 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           named_bar_sync(1, 128);
           const uint32_t bs = smem_u32(sBias + ch * 64);
           const uint32_t rowp = smem_u32(stg + row * 128);
-          epilogue_half(v0, bs, rowp, row, 0, stat_row ? stat_row + (ch * 64) * 2 : nullptr, lane);
-          epilogue_half(v1, bs + 128, rowp, row, 4, stat_row ? stat_row + (ch * 64 + 32) * 2 : nullptr, lane);
+          epilogue_half(v0, bs, rowp, row, 0, stat_row ? my_stat : nullptr, lane);
+          epilogue_half(v1, bs + 128, rowp, row, 4, stat_row ? my_stat + 64 : nullptr, lane);
           fence_proxy_async_smem();
           named_bar_sync(2, 128);
+          if (stat_row) stats_combine_store(sStat, 64, static_cast<int>(threadIdx.x) - 64, stat_row + (ch * 64) * 2);
           if (leader) {
             tma_store_4d(&p.out_map, stg, ch * 64, w0, h0, n);
             tma_store_commit();
@@ -500,8 +516,9 @@ struct HaloCfg {
   static constexpr int kSsFloats = 2 * 512;   // scale/shift of up to 512 transformed channels
   static constexpr int kTmemCols = (2 * N <= 32) ? 32 : ((2 * N <= 64) ? 64 : ((2 * N <= 128) ? 128 : ((2 * N <= 256) ? 256 : 512)));
   static constexpr int kStatScratch = (FD_EPI_STATS_SMEM && !OUT4) ? 4 * 32 * 36 * 4 : 0;   // per epilogue warp: 32 x 36 floats
+  static constexpr int kStatBytes = OUT4 ? 0 : 4 * 64 * 2 * 4;                              // per-warp column sums of one chunk
   static constexpr int kSmemBytes = 1024 + kStagesA * kHaloStageBytes + kStagesB * kBBytes + kOutBytes + N * 4 +
-                                    kSsFloats * 4 + 512 + kStatScratch;
+                                    kSsFloats * 4 + 512 + kStatScratch + kStatBytes;
   static_assert(kBBytes % 1024 == 0, "B stage must keep the 1024-byte swizzle alignment");
   static_assert(OUTC == 0 || (OUTC == 4 && N == 16) || (OUTC == 36 && N == 48), "fp32 pixel-major forms: 4 of 16 or 36 of 48 columns");
 };
@@ -707,6 +724,9 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
     // per-warp 32 x 36-float tile behind the barrier block (column statistics by shared-memory transpose)
     const uint32_t stat_scratch =
         FD_EPI_STATS_SMEM ? smem_u32(reinterpret_cast<uint8_t*>(bars) + 512) + static_cast<uint32_t>(ew) * 4608u : 0u;
+    float* sStat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512 + Cfg::kStatScratch);
+    float* my_stat = sStat + ew * 128;
+    const int et = static_cast<int>(threadIdx.x) - 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
@@ -746,8 +766,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
         }
       } else if constexpr (TF32) {
         constexpr int kChunks = N / 32;           // 32 fp32 channels = one 128-byte staging row
-        const int slab = rem * 4 + ew;
-        float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * (tiles_per_img * 4) + slab) * N) * 2 : nullptr;
+        float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * tiles_per_img + rem) * N) * 2 : nullptr;
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ++ch) {
           uint8_t* stg = sOut + (ch & 1) * (kTileM * 128);
@@ -761,9 +780,10 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
             mbar_arrive_remote(&tempty_bar[acc], 0);
           }
           epilogue_chunk_f32(v, smem_u32(sBias + ch * 32), smem_u32(stg + row * 128), row,
-                             stat_row ? stat_row + (ch * 32) * 2 : nullptr, lane, stat_scratch);
+                             stat_row ? my_stat : nullptr, lane, stat_scratch);
           fence_proxy_async_smem();
           named_bar_sync(2, 128);
+          if (stat_row) stats_combine_store(sStat, 32, et, stat_row + (ch * 32) * 2);
           if (leader) {
             tma_store_4d(&p.out_map, stg, ch * 32, w0, h0, n);
             tma_store_commit();
@@ -771,8 +791,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
         }
       } else {
       constexpr int kChunks = N / 64;
-      const int slab = rem * 4 + ew;
-      float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * (tiles_per_img * 4) + slab) * N) * 2 : nullptr;
+      float* stat_row = p.stats ? p.stats + ((static_cast<size_t>(n) * tiles_per_img + rem) * N) * 2 : nullptr;
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ++ch) {
         uint8_t* stg = sOut + (ch & 1) * (kTileM * 128);
@@ -785,18 +804,18 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + ch * 64, v);
           tmem_ld_wait();
-          epilogue_half(v, bs, rowp, row, 0, stat_row ? stat_row + (ch * 64) * 2 : nullptr, lane, stat_scratch);
+          epilogue_half(v, bs, rowp, row, 0, stat_row ? my_stat : nullptr, lane, stat_scratch);
           tmem_ld_32x32b_x32(t_row + ch * 64 + 32, v);
           tmem_ld_wait();
           if (ch == kChunks - 1) {
             tc_fence_before_sync();
             mbar_arrive_remote(&tempty_bar[acc], 0);
           }
-          epilogue_half(v, bs + 128, rowp, row, 4, stat_row ? stat_row + (ch * 64 + 32) * 2 : nullptr, lane,
-                        stat_scratch);
+          epilogue_half(v, bs + 128, rowp, row, 4, stat_row ? my_stat + 64 : nullptr, lane, stat_scratch);
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
+        if (stat_row) stats_combine_store(sStat, 64, et, stat_row + (ch * 64) * 2);
         if (leader) {
           tma_store_4d(&p.out_map, stg, ch * 64, w0, h0, n);
           tma_store_commit();

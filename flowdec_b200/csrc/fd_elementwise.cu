@@ -137,18 +137,30 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
   const int C = C1 + C2;
   const int cpg = C / groups;
   double s = 0.0, q = 0.0;
-  // channels of the group may straddle the concat seam: walk them one by one, slabs strided
-  for (int ci = 0; ci < cpg; ++ci) {
-    const int c = g * cpg + ci;
-    const bool first = c < C1;
-    const int S = first ? S1 : S2;
-    const int Cs = first ? C1 : C2;
-    const int cc = first ? c : c - C1;
-    const float* base = (first ? part1 : part2) + (static_cast<size_t>(b) * S * Cs + cc) * 2;
+  // The group's channels are contiguous inside a source (a group may straddle the concat seam: then it has one
+  // run in each source).  A thread walks whole slabs — the run's (sum, sumsq) pairs are adjacent floats, so the
+  // reads are full sectors even when a producer left one slab per conv tile (S up to a few thousand) — in a
+  // fixed order; the block tree below is fixed too, so the result does not depend on the batch composition.
+  for (int src = 0; src < 2; ++src) {
+    const int Cs = src == 0 ? C1 : C2;
+    const int S = src == 0 ? S1 : S2;
+    const float* part = src == 0 ? part1 : part2;
+    const int g_lo = g * cpg, g_hi = g_lo + cpg;              // virtual channel range of the group
+    const int lo = max(g_lo, src == 0 ? 0 : C1) - (src == 0 ? 0 : C1);
+    const int hi = min(g_hi, src == 0 ? C1 : C) - (src == 0 ? 0 : C1);
+    if (Cs == 0 || hi <= lo) continue;
+    const float* base = part + (static_cast<size_t>(b) * S * Cs + lo) * 2;
+    const int n2 = (hi - lo);                                  // float2 pairs per slab
     for (int sl = threadIdx.x; sl < S; sl += 128) {
-      const float2 v = *reinterpret_cast<const float2*>(base + static_cast<size_t>(sl) * Cs * 2);
-      s += static_cast<double>(v.x);
-      q += static_cast<double>(v.y);
+      const float2* row = reinterpret_cast<const float2*>(base + static_cast<size_t>(sl) * Cs * 2);
+      float fs = 0.f, fq = 0.f;
+      for (int i = 0; i < n2; ++i) {
+        const float2 v = row[i];
+        fs += v.x;
+        fq += v.y;
+      }
+      s += static_cast<double>(fs);
+      q += static_cast<double>(fq);
     }
   }
   ssum[threadIdx.x] = s;

@@ -54,8 +54,8 @@ def pack_conv_weight(segments, npad, tf32=False):
 
 
 def conv_stats_slabs(H, W):
-    """number of partial-sum slabs the conv epilogue writes per sample (4 warps x 128-pixel tiles)"""
-    return 4 * (H * W // 128)
+    """number of partial-sum slabs the conv epilogue writes per sample: one per 128-pixel tile"""
+    return H * W // 128
 
 
 def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None, algo_cout=None):
