@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config3 / config4 / shard-check records")
     ap.add_argument("--streams", type=int, default=0, help="micro-batches in flight (0 = model default)")
+    ap.add_argument("--max-frames", type=int, default=0, help="padded STFT frames per backbone pass (0 = model default)")
     return ap.parse_args()
 
 
@@ -275,6 +276,8 @@ def main():
         model.max_batch = args.max_batch
     if args.streams:
         model.overlap_streams = args.streams
+    if args.max_frames:
+        model.max_frames_per_pass = args.max_frames
     L = int(args.seconds * SR)
     B = args.batch
     nfe = nfe_of(args.N, args.solver)

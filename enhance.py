@@ -156,6 +156,8 @@ def main(argv=None):
                 y, sr = load_wav(path)
                 if y.shape[-1] / sr > 30.0:                    # reference enhance.py:115,138-139
                     print("Skipping file due to length:", path)
+                    if trf is not None:                        # the reference still lists the (unwritten) triple
+                        print(f"{clean[i]} ---> {noisy[i]} ---> {out_path}", file=trf)
                     continue
                 if sr != model.sampling_rate:
                     import torchaudio

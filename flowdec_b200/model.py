@@ -392,11 +392,16 @@ class ScoreModel(EnhancementModel):
                 probability_flow=False, noise=None, **kwargs):
         """reference model.py:630-657.  `noise`: optional list of complex64 [B,1,768,Tp] tensors standing
         in for the sampler's draws, in call order: prior, then per step (corrector draws..., predictor draw)."""
-        if sampler_type != "pc" or predictor != "reverse_diffusion" or corrector not in ("ald", "none"):
-            raise NotImplementedError("flowdec_b200.ScoreModel implements the PC sampler with "
-                                      "reverse_diffusion predictor and ald / none corrector")
-        if probability_flow:
-            raise NotImplementedError("probability_flow=True is not implemented")
+        if sampler_type != "pc" or predictor not in ("reverse_diffusion", "euler_maruyama") or \
+                corrector not in ("ald", "none"):
+            raise NotImplementedError("flowdec_b200.ScoreModel implements the PC sampler with the reverse_diffusion / "
+                                      "euler_maruyama predictors and the ald / none correctors (the scipy RK45 "
+                                      "'ode' sampler of sampling/__init__.py:75-147 is host-driven and out of scope)")
+        # For the OUVE SDE the two predictors are the same update: Euler-Maruyama (predictors.py:47-59) steps
+        # x + [theta (y - x) - g^2 score] (-1/N) + g sqrt(1/N) z, reverse diffusion (predictors.py:61-71) steps
+        # x - [theta (y - x)/N - G^2 score] + G z with G = g sqrt(1/N) (sdes.py:68-76): identical coefficients.
+        # probability_flow (sdes.py:107-123): half the score term, no predictor noise.
+        pf = 0.5 if probability_flow else 1.0
         if corrector == "none":
             corrector_steps = 0
         dev = self.device
@@ -455,13 +460,16 @@ class ScoreModel(EnhancementModel):
             th_dt, G = sde.discretize(t)
             th_dt, G = float(th_dt), float(G)
             last = (i == N - 1)
+            # the reference draws z in every predictor step (randn_like) even when it is multiplied by zero
             z = None if (last and denoise) else draw()
+            Gz = 0.0 if probability_flow else G
             if last:
-                backbone_stage(x, t, x_mean, 1.0 + th_dt, -th_dt, None, 0.0, -G * G / std)
-                if not denoise:
+                backbone_stage(x, t, x_mean, 1.0 + th_dt, -th_dt, None, 0.0, -pf * G * G / std)
+                if not denoise and not probability_flow:
                     ops.x0_noise(x_mean, ones64, z, G, x_mean)
             else:
-                backbone_stage(x, t, xn, 1.0 + th_dt, -th_dt, z, G, -G * G / std)
+                backbone_stage(x, t, xn, 1.0 + th_dt, -th_dt, z if not probability_flow else None, Gz,
+                               -pf * G * G / std)
                 x, xn = xn, x
         out = torch.empty(B * C, L, **f32)
         fe.istft_decompress(x_mean, L, nf, out)
