@@ -64,6 +64,18 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
+// Snake1d: x + sin^2(a x) / (a + 1e-9) = x + (1 - cos(2 a x)) * 0.5 / (a + 1e-9).  cos through one MUFU op after
+// an explicit reduction of the argument to [-pi, pi] (2 FMAs; cos.approx alone loses accuracy for large arguments):
+// absolute error ~1e-6 of the sin^2 term, three orders below the tf32 rounding of the stored activation.  sinf()
+// in the epilogue cost ~40 instructions per element and made the 48 kHz layers epilogue-bound (profiles/r2_ndac_*).
+__device__ __forceinline__ float snake_fast(float x, float two_alpha, float half_inv) {
+  const float z = two_alpha * x;
+  const float k = rintf(z * 0.15915494309189535f);                 // z / 2 pi
+  float r = fmaf(k, -6.2831854820251465f, z);                      // z - k * fl(2 pi)
+  r = fmaf(k, 1.7484555e-7f, r);                                   // ... - k * (2 pi - fl(2 pi))
+  return fmaf(1.0f - __cosf(r), half_inv, x);
+}
+
 __global__ void __launch_bounds__(224, 1) dac_conv_tc_kernel(const __grid_constant__ DacTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -185,18 +197,25 @@ __global__ void __launch_bounds__(224, 1) dac_conv_tc_kernel(const __grid_consta
         sBias[c] = p.bias ? p.bias[n0 + c] : 0.f;
         if (p.has_act) {
           const float a = p.alpha[(n0 + c) % p.alpha_mod];
-          sAlpha[c] = a;
-          sInv[c] = 1.0f / (a + 1e-9f);
+          sAlpha[c] = 2.0f * a;                      // snake_fast takes 2 alpha and 0.5 / (alpha + 1e-9)
+          sInv[c] = 0.5f / (a + 1e-9f);
         }
       }
       named_bar_sync(3, 128);
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after_sync();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * 256);
       const float* res_row = (p.residual != nullptr && t < p.T_out)
                                  ? p.residual + static_cast<size_t>(b) * p.res_bstride + static_cast<size_t>(t) * p.Ntot + n0
                                  : nullptr;
       const int chunks = p.N / 32;
+      // the residual of chunk 0 is requested before waiting for the accumulator (its latency hides behind the MMAs);
+      // later chunks request theirs one chunk ahead
+      float4 rr[8];
+      if (res_row != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rr[i] = *reinterpret_cast<const float4*>(res_row + i * 4);
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * 256);
 #pragma unroll 1
       for (int ch = 0; ch < chunks; ++ch) {
         uint32_t v[32];
@@ -206,19 +225,22 @@ __global__ void __launch_bounds__(224, 1) dac_conv_tc_kernel(const __grid_consta
           tc_fence_before_sync();
           mbar_arrive(&tempty[acc]);
         }
-        // the TMA stores that read the staging tiles of the previous chunk must have drained them
-        if (leader) tma_store_wait_read<0>();
-        named_bar_sync(1, 128);
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + sBias[ch * 32 + i];
         if (res_row != nullptr) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 r = *reinterpret_cast<const float4*>(res_row + ch * 32 + i * 4);
-            f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w;
+            f[4 * i] += rr[i].x; f[4 * i + 1] += rr[i].y; f[4 * i + 2] += rr[i].z; f[4 * i + 3] += rr[i].w;
+          }
+          if (ch + 1 < chunks) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rr[i] = *reinterpret_cast<const float4*>(res_row + (ch + 1) * 32 + i * 4);
           }
         }
+        // the TMA stores that read the staging tiles of the previous chunk must have drained them
+        if (leader) tma_store_wait_read<0>();
+        named_bar_sync(1, 128);
         const uint32_t rowp = smem_u32(sOut + row * 128);
         if (p.has_raw) {
 #pragma unroll
@@ -232,9 +254,8 @@ __global__ void __launch_bounds__(224, 1) dac_conv_tc_kernel(const __grid_consta
         if (p.has_act) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float sn = sinf(sAlpha[ch * 32 + i] * f[i]);
             // the activated tensor only ever feeds a tf32 MMA: round to nearest here (the pipe would truncate)
-            f[i] = round_tf32(fmaf(sn * sn, sInv[ch * 32 + i], f[i]));
+            f[i] = round_tf32(snake_fast(f[i], sAlpha[ch * 32 + i], sInv[ch * 32 + i]));
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {

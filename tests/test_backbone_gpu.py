@@ -210,3 +210,26 @@ def test_config2_full_size_properties(model):
     keep = [i for i in range(B) if i != 5]
     assert torch.equal(half[keep], 0.5 * out[keep])
     assert torch.equal(half[5], out[5])          # the all-zero clip is normalised by 1 either way (util/other.py:77)
+
+
+def test_caches_are_bounded_over_many_lengths(model):
+    """enhance.py's one-file-per-call loop over files of different lengths must not grow GPU memory without bound:
+    clips of one padded-frame bucket share a cache entry, entries and backbone workspaces are evicted LRU"""
+    from flowdec_b200.util.synth import synth_waveforms
+    model.reset_cache()
+    outs = {}
+    for L in (24000, 24100, 30000, 50000, 50500, 75000, 99000, 125000, 24000):
+        y = synth_waveforms(1, L, seed=L)
+        g = torch.Generator().manual_seed(L)
+        from flowdec_b200.util.other import padded_frames
+        eps = torch.randn(1, 1, 768, padded_frames(1 + L // 384), dtype=torch.complex64, generator=g)
+        x = model.enhance(y, N=1, solver="euler", noise=eps)
+        assert x.shape == y.shape and torch.isfinite(x).all()
+        if L in outs:                                    # evicted and rebuilt: same result
+            assert torch.equal(outs[L], x)
+        outs[L] = x
+        assert len(model._graphs) <= model.graph_cache_size
+        assert len(model.backbone._workspaces) <= max(model.backbone.max_workspaces, 2 * model.graph_cache_size)
+    # 24000 and 24100 fall into the same 64-frame bucket -> one entry served both
+    keys = {k[1] for k in model._graphs}
+    assert len(keys) == len(model._graphs)

@@ -74,6 +74,8 @@ def test_from_codes_and_decode(latent, dim, rates, nq, T):
     sd = D.synth_dac_state_dict(latent, dim, rates, nq, seed=1)
     model = DAC(sd, decoder_dim=dim, decoder_rates=rates, n_codebooks=nq, latent_dim=latent,
                 sample_rate=48000).to("cuda").eval()
+    # built on the CPU, moved with .to("cuda"): every tensor the op lists resolve to must have followed (round-1 bug)
+    assert all(t.is_cuda for t in model.op_tensors().values())
     g = torch.Generator().manual_seed(2)
     codes = torch.randint(0, 1024, (2, nq, T), generator=g)
     sd64 = {k: v.double() for k, v in sd.items()}
