@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip the config3 / config4 / shard-check records")
     ap.add_argument("--streams", type=int, default=0, help="micro-batches in flight (0 = model default)")
     ap.add_argument("--max-frames", type=int, default=0, help="padded STFT frames per backbone pass (0 = model default)")
+    ap.add_argument("--max-ctas", type=int, default=0, help="CTAs of the persistent conv kernels (0 = one per SM)")
     return ap.parse_args()
 
 
@@ -278,6 +279,8 @@ def main():
         model.overlap_streams = args.streams
     if args.max_frames:
         model.max_frames_per_pass = args.max_frames
+    if args.max_ctas:
+        model.backbone.max_ctas = args.max_ctas
     L = int(args.seconds * SR)
     B = args.batch
     nfe = nfe_of(args.N, args.solver)
