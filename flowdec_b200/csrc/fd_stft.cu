@@ -226,6 +226,12 @@ __global__ void __launch_bounds__(384) istft_decompress_kernel(const float2* __r
 
 }  // namespace fd
 
+namespace fd {   // fd_stft_pfa.cu
+int stft_pfa_enabled();
+int stft_pfa_launch(const float* y, int B, int L, const int* lengths, const float* normfac, const float* window,
+                    const void* tw, float alpha, float beta, int frames, int Tp, void* out, cudaStream_t stream);
+}  // namespace fd
+
 using namespace fd;
 
 extern "C" int fd_twiddles1534(void* tw, cudaStream_t stream) {
@@ -251,6 +257,8 @@ extern "C" int fd_stft1534_compress(const float* y, int B, int L, const float* n
   FD_REQUIRE(L > kPad, "fd_stft1534_compress: L=%d must exceed the reflect pad %d", L, kPad);
   const int frames = 1 + L / kHop;
   FD_REQUIRE(Tp >= frames, "fd_stft1534_compress: Tp=%d < frames=%d", Tp, frames);
+  if (stft_pfa_enabled() && Tp % 4 == 0)      // prime-factor FFT (fd_stft_pfa.cu); the direct DFT below is the A/B path
+    return stft_pfa_launch(y, B, L, nullptr, normfac, window, tw, alpha, beta, frames, Tp, out, stream);
   dim3 grid((Tp + kStftFrames - 1) / kStftFrames, kBins / 64, B);
   stft_compress_kernel<<<grid, 256, 0, stream>>>(y, L, nullptr, normfac, window,
                                                  static_cast<const float2*>(tw), alpha, beta, frames, Tp,
@@ -263,6 +271,8 @@ extern "C" int fd_stft1534_compress_ragged(const float* y, int B, int L, const i
                                            float alpha, float beta, int Tp, void* out, cudaStream_t stream) {
   FD_REQUIRE(lengths != nullptr && L > kPad, "fd_stft1534_compress_ragged: lengths NULL or pitch %d <= %d", L, kPad);
   FD_REQUIRE(Tp >= 1, "fd_stft1534_compress_ragged: Tp=%d", Tp);
+  if (stft_pfa_enabled() && Tp % 4 == 0)
+    return stft_pfa_launch(y, B, L, lengths, normfac, window, tw, alpha, beta, 0, Tp, out, stream);
   dim3 grid((Tp + kStftFrames - 1) / kStftFrames, kBins / 64, B);
   stft_compress_kernel<<<grid, 256, 0, stream>>>(y, L, lengths, normfac, window,
                                                  static_cast<const float2*>(tw), alpha, beta, 0, Tp,

@@ -82,9 +82,9 @@ class AmplitudeCompressedComplexSTFT(InvertibleFeatureExtractor):
         return ops.stft_compress(y2d, normfac, self.complex_stft.window, self.twiddles(), self.alpha, self.beta, out,
                                  lengths=lengths)
 
-    def istft_decompress(self, X, L, normfac, out, lengths=None):
+    def istft_decompress(self, X, L, normfac, out, lengths=None, ws=None):
         return ops.istft_decompress(X, L, self.complex_stft.window, self.twiddles(), normfac, self.alpha,
-                                    self.beta, out, lengths=lengths)
+                                    self.beta, out, lengths=lengths, ws=ws)
 
     # reference-shaped API ---------------------------------------------------------------------
     def forward(self, x, comp_eps=None, **kwargs):

@@ -208,7 +208,7 @@ class FlowModel(EnhancementModel):
             cur ^= 1
             if want_traj:
                 traj.append(st["x"][cur].clone())
-        fe.istft_decompress(st["x"][cur], L, st["nf"], st["out"], lengths=lens)
+        fe.istft_decompress(st["x"][cur], L, st["nf"], st["out"], lengths=lens, ws=st["fr"])
         return traj
 
     def _static(self, B, Tp, dev):
@@ -220,7 +220,8 @@ class FlowModel(EnhancementModel):
                     len=torch.empty(B, device=dev, dtype=torch.int32),
                     Y=torch.empty(B, 768, Tp, 2, **f32), eps=torch.empty(B, 768, Tp, 2, **f32),
                     x=[torch.empty(B, 768, Tp, 2, **f32) for _ in range(2)],
-                    tmp=torch.empty(B, 768, Tp, 2, **f32), out=torch.empty(B, L, **f32))
+                    tmp=torch.empty(B, 768, Tp, 2, **f32), out=torch.empty(B, L, **f32),
+                    fr=torch.empty(B, Tp, 1536, **f32))      # iSTFT workspace: windowed frames before overlap-add
 
     def _entry(self, B, Tp, N, solver, sigma_fac, dev):
         # the micro-batch split and the lane count are baked into a captured graph

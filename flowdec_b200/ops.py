@@ -371,8 +371,30 @@ def stft_compress(y2d, nf, window, tw, alpha, beta, out, lengths=None):
     return out
 
 
-def istft_decompress(X, L, window, tw, nf, alpha, beta, out, lengths=None):
+STFT_PFA = True     # prime-factor FFT kernels (csrc/fd_stft_pfa.cu); False = the direct-DFT kernels (A/B, tests)
+
+
+def stft_use_pfa(on):
+    """selects the STFT / iSTFT algorithm in the library AND in these wrappers; returns the previous setting"""
+    global STFT_PFA
+    prev = STFT_PFA
+    STFT_PFA = bool(on)
+    _lib.lib().fd_stft_use_pfa(int(STFT_PFA))
+    return prev
+
+
+def istft_decompress(X, L, window, tw, nf, alpha, beta, out, lengths=None, ws=None):
+    """ws: optional fp32 workspace [B, Tp, 1536] (static buffers of a captured graph pass theirs)"""
     B, Tp = X.shape[0], X.shape[2]
+    if STFT_PFA and Tp % 4 == 0:
+        if ws is None:
+            ws = torch.empty(B, Tp, 1536, device=X.device, dtype=torch.float32)
+        assert ws.is_contiguous() and ws.numel() >= B * Tp * 1536
+        rc = _lib.lib().fd_istft1534_decompress_pfa(_lib.ptr(X), B, Tp, L, _lib.ptr(lengths), _lib.ptr(window),
+                                                    _lib.ptr(tw), _lib.ptr(nf), ctypes.c_float(alpha),
+                                                    ctypes.c_float(beta), _lib.ptr(ws), _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(rc, "fd_istft1534_decompress_pfa")
+        return out
     if lengths is None:
         rc = _lib.lib().fd_istft1534_decompress(_lib.ptr(X), B, Tp, L, _lib.ptr(window), _lib.ptr(tw), _lib.ptr(nf),
                                                 ctypes.c_float(alpha), ctypes.c_float(beta), _lib.ptr(out),

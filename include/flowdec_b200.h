@@ -132,6 +132,14 @@ int fd_stft1534_compress(const float* y, int B, int L, const float* normfac, con
 /* inverse: decompress, overlap-add iSTFT (torch.istft semantics incl. length=L), times normfac */
 int fd_istft1534_decompress(const void* X, int B, int Tp, int L, const float* window, const void* tw,
                             const float* normfac, float alpha, float beta, float* out, fd_stream_t stream);
+/* STFT / iSTFT algorithm: 1 (default) = prime-factor FFT (1534 = 26 x 59, fd_stft_pfa.cu; needs Tp % 4 == 0, which
+ * pad_spec's multiple of 64 always gives), 0 = direct DFT.  Returns the previous setting. */
+int fd_stft_use_pfa(int on);
+/* iSTFT through the prime-factor kernels: same contract as fd_istft1534_decompress(_ragged) (lengths may be NULL) plus
+ * a caller-owned workspace frames_ws of B * Tp * 1536 floats (windowed time-domain frames before overlap-add). */
+int fd_istft1534_decompress_pfa(const void* X, int B, int Tp, int L, const int* lengths, const float* window,
+                                const void* tw, const float* normfac, float alpha, float beta, float* frames_ws,
+                                float* out, fd_stream_t stream);
 /* ragged batches (length-bucketed batching across files): rows of pitch L hold clips of
  * lengths[b] <= L samples (int32 [B], device; every lengths[b] > 767 and 1 + lengths[b]/384 <= Tp, checked by
  * the caller).  Each clip gets exactly the frames, reflect padding, normalisation and istft(length=) it would

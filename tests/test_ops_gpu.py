@@ -183,9 +183,17 @@ def test_time_embedding_matvec():
         assert rel_l2(te.cpu(), ref) < 2e-5, (t, rel_l2(te.cpu(), ref))
 
 
+@pytest.fixture(params=[True, False], ids=["pfa_fft", "direct_dft"])
+def stft_algo(request):
+    """both STFT / iSTFT implementations: the prime-factor FFT (default) and the direct DFT"""
+    old = ops.stft_use_pfa(request.param)
+    yield request.param
+    ops.stft_use_pfa(old)
+
+
 @pytest.mark.parametrize("L,kind", [(24000, "tones"), (48000, "gauss"), (30011, "tones"), (768, "gauss"), (24000, "zeros"),
                                     (96000, "tones"), (61001, "gauss")])
-def test_stft_istft_vs_oracle(L, kind):
+def test_stft_istft_vs_oracle(L, kind, stft_algo):
     B = 2
     y = synth_waveforms(B, L, seed=99, kind=kind)
     fe = AmplitudeCompressedComplexSTFT("hann", 1534, 48000, alpha=0.3, beta=0.33, n_hops=4).to(DEV)
