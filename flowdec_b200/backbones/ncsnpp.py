@@ -214,7 +214,7 @@ class NCSNpp(nn.Module):
         # (lane, B, F, T) -> _Workspace, least recently used first; signatures in `_pinned` (those of live CUDA
         # graphs, set by FlowModel) are never evicted, others beyond `max_workspaces` are
         self._workspaces = OrderedDict()
-        self._pinned = set()
+        self._pins, self._pinned = {}, set()
         self.max_workspaces = 4
         self._ws_cur = None
         self.stats_slabs = 64
@@ -268,10 +268,11 @@ class NCSNpp(nn.Module):
         return super()._apply(fn, *a, **k)
 
     # ------------------------------------------------------------------ workspaces
-    def pin_workspaces(self, sigs):
-        """sigs: set of (micro-batch, F, T) whose workspaces must keep their addresses (captured CUDA graphs
-        replay into them); everything else becomes evictable"""
-        self._pinned = set(sigs)
+    def pin_workspaces(self, sigs, owner="default"):
+        """sigs: set of (micro-batch, F, T) whose workspaces must keep their addresses (captured CUDA graphs of
+        `owner` replay into them; several models may share one backbone); everything unpinned becomes evictable"""
+        self._pins[owner] = set(sigs)
+        self._pinned = set().union(*self._pins.values())
         self._evict()
 
     def _evict(self):

@@ -124,7 +124,7 @@ class FlowModel(EnhancementModel):
         self._graphs = OrderedDict()
         self._sig_cache = None
         if hasattr(self.backbone, "pin_workspaces"):
-            self.backbone.pin_workspaces(set())
+            self.backbone.pin_workspaces(set(), owner=id(self))
 
     def _apply(self, fn, *a, **k):
         self.reset_cache()
@@ -235,7 +235,7 @@ class FlowModel(EnhancementModel):
             self._graphs[key] = entry
             if hasattr(self.backbone, "pin_workspaces"):
                 # workspaces of evicted entries become collectable; live graphs keep theirs (stable addresses)
-                self.backbone.pin_workspaces(set().union(*[e["sigs"] for e in self._graphs.values()]))
+                self.backbone.pin_workspaces(set().union(*[e["sigs"] for e in self._graphs.values()]), owner=id(self))
         else:
             self._graphs.move_to_end(key)
         return entry
@@ -376,6 +376,8 @@ class ScoreModel(EnhancementModel):
         self.sde = sde
         self.t_eps = t_eps
         self.max_batch = 8
+        self.use_cuda_graph = True
+        self._sgraphs = OrderedDict()     # static buffers + CUDA graph per (batch, length, N, corrector_steps, ...), LRU of 2
 
     def sde_std(self, t_batch):
         t = float(t_batch.flatten()[0]) if torch.is_tensor(t_batch) else float(t_batch)
@@ -386,13 +388,74 @@ class ScoreModel(EnhancementModel):
         std = float(self.sde_std(t_batch))
         return -self.backbone(xt, y, t_batch) / std
 
+    def reset_cache(self):
+        self._sgraphs = OrderedDict()
+        if hasattr(self.backbone, "pin_workspaces"):
+            self.backbone.pin_workspaces(set(), owner=id(self))
+
+    def _apply(self, fn, *a, **k):
+        self.reset_cache()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict=None, **kw):
+        self.reset_cache()
+        return super().load_state_dict(state_dict, strict=self.strict_loading if strict is None else strict, **kw)
+
+    def _sampler(self, st, N, corrector_steps, snr, denoise, probability_flow):
+        """the whole PC sampler on static buffers (graph-capturable): draws come from st["z"][i] in call order"""
+        fe, bb, sde = self.feature_extractor, self.backbone, self.sde.copy()
+        sde.N = N
+        B, L, Tp = st["B"], st["L"], st["Tp"]
+        Y, x, xn, x_mean, z = st["Y"], st["x"], st["xn"], st["x_mean"], st["z"]
+        pf = 0.5 if probability_flow else 1.0
+        ops.normfac(st["y"], 1 if self.normalize_mode == "noisy" else 0, st["nf"])
+        fe.stft_compress(st["y"], st["nf"], Y)
+        mb = max(1, min(self.max_batch, 4096 // Tp))
+        nz = iter(range(z.shape[0]))
+
+        def backbone_stage(x, t, out, c1, c2, base3, c3, coef):
+            for lo in range(0, B, mb):
+                hi = min(B, lo + mb)
+                bb.velocity(x[lo:hi], Y[lo:hi], float(t), out=out[lo:hi], base1=x[lo:hi], c1=c1,
+                            base2=Y[lo:hi], c2=c2, base3=base3[lo:hi] if base3 is not None else None,
+                            c3=c3, coef=coef)
+
+        # prior: x_T = y + z * std(T)     (sdes.py:201-206); x0_kernel with a unit sigma vector is out = Y + fac*z
+        ops.x0_noise(Y, st["ones64"], z[next(nz)], float(sde._std(1.0)), x)
+        timesteps = torch.linspace(sde.T, self.t_eps, N).numpy()
+        for i in range(N):
+            t = timesteps[i]
+            std = float(sde._std(t))
+            for _ in range(corrector_steps):
+                # ALD (correctors.py:54-66): x <- x + step*score + sqrt(2 step) z, score = -v/std
+                step = (snr * std) ** 2 * 2
+                backbone_stage(x, t, xn, 1.0, 0.0, z[next(nz)], float(np.sqrt(np.float32(step * 2))), -step / std)
+                x, xn = xn, x
+            # reverse diffusion (predictors.py:66-71, sdes.py:118-123):
+            #   rev_f = theta dt (y - x) - G^2 score ; x_mean = x - rev_f ; x = x_mean + G z
+            th_dt, G = sde.discretize(t)
+            th_dt, G = float(th_dt), float(G)
+            last = (i == N - 1)
+            zi = None if (last and denoise) else z[next(nz)]
+            if last:
+                backbone_stage(x, t, x_mean, 1.0 + th_dt, -th_dt, None, 0.0, -pf * G * G / std)
+                if not denoise and not probability_flow:
+                    ops.x0_noise(x_mean, st["ones64"], zi, G, x_mean)
+            else:
+                backbone_stage(x, t, xn, 1.0 + th_dt, -th_dt, zi if not probability_flow else None,
+                               0.0 if probability_flow else G, -pf * G * G / std)
+                x, xn = xn, x
+        fe.istft_decompress(x_mean, L, st["nf"], st["out"], ws=st["fr"])
+
     @torch.no_grad()
     @_on_model_device
     def enhance(self, y, sampler_type="pc", predictor="reverse_diffusion", corrector="ald", N=30,
                 corrector_steps=1, snr=0.5, return_preprocess_info=False, denoise=True,
                 probability_flow=False, noise=None, **kwargs):
         """reference model.py:630-657.  `noise`: optional list of complex64 [B,1,768,Tp] tensors standing
-        in for the sampler's draws, in call order: prior, then per step (corrector draws..., predictor draw)."""
+        in for the sampler's draws, in call order: prior, then per step (corrector draws..., predictor draw).
+        All draws of a call are made up front into a static buffer, so the sampler loop (N x (1 + corrector_steps)
+        backbone evaluations with their fused updates) replays as ONE CUDA graph per (batch, length, N, ...)."""
         if sampler_type != "pc" or predictor not in ("reverse_diffusion", "euler_maruyama") or \
                 corrector not in ("ald", "none"):
             raise NotImplementedError("flowdec_b200.ScoreModel implements the PC sampler with the reverse_diffusion / "
@@ -402,7 +465,6 @@ class ScoreModel(EnhancementModel):
         # x + [theta (y - x) - g^2 score] (-1/N) + g sqrt(1/N) z, reverse diffusion (predictors.py:61-71) steps
         # x - [theta (y - x)/N - G^2 score] + G z with G = g sqrt(1/N) (sdes.py:68-76): identical coefficients.
         # probability_flow (sdes.py:107-123): half the score term, no predictor noise.
-        pf = 0.5 if probability_flow else 1.0
         if corrector == "none":
             corrector_steps = 0
         dev = self.device
@@ -414,72 +476,57 @@ class ScoreModel(EnhancementModel):
             y = y.unsqueeze(0)
             squeeze_dims += 1
         B, C, L = y.shape
-        fe, bb, sde = self.feature_extractor, self.backbone, self.sde.copy()
-        sde.N = N
+        if L <= 767:
+            raise ValueError(f"waveform length {L} must exceed the STFT reflect pad (767)")
         Tp = padded_frames(1 + L // 384)
-        f32 = dict(device=dev, dtype=torch.float32)
-        y2 = y.reshape(B * C, L).to(dev, torch.float32).contiguous()
-        nf = torch.empty(B * C, **f32)
-        Y = torch.empty(B * C, 768, Tp, 2, **f32)
-        ops.normfac(y2, 1 if self.normalize_mode == "noisy" else 0, nf)
-        fe.stft_compress(y2, nf, Y)
-        draws = iter(noise) if noise is not None else None
-
-        def draw():
-            if draws is not None:
-                z = next(draws).to(dev, torch.complex64).reshape(B * C, 768, Tp)
-            else:
-                z = torch.randn(B * C, 768, Tp, dtype=torch.complex64, device=dev)
-            return torch.view_as_real(z).contiguous()
-
-        mb = max(1, min(self.max_batch, 4096 // Tp))
-
-        def backbone_stage(x, t, out, c1, c2, base3, c3, coef):
-            for lo in range(0, B * C, mb):
-                hi = min(B * C, lo + mb)
-                bb.velocity(x[lo:hi], Y[lo:hi], float(t), out=out[lo:hi], base1=x[lo:hi], c1=c1,
-                            base2=Y[lo:hi], c2=c2, base3=base3[lo:hi] if base3 is not None else None,
-                            c3=c3, coef=coef)
-
-        # prior: x_T = y + z * std(T)     (sdes.py:201-206); x0_kernel with a unit sigma vector is out = Y + fac*z
-        x = torch.empty_like(Y)
-        xn = torch.empty_like(Y)
-        x_mean = torch.empty_like(Y)
-        ones64 = torch.ones(768, device=dev, dtype=torch.float64)
-        ops.x0_noise(Y, ones64, draw(), float(sde._std(1.0)), x)
-        timesteps = torch.linspace(sde.T, self.t_eps, N).numpy()
-        for i in range(N):
-            t = timesteps[i]
-            std = float(sde._std(t))
-            for _ in range(corrector_steps):
-                # ALD (correctors.py:54-66): x <- x + step*score + sqrt(2 step) z, score = -v/std
-                step = (snr * std) ** 2 * 2
-                backbone_stage(x, t, xn, 1.0, 0.0, draw(), float(np.sqrt(np.float32(step * 2))), -step / std)
-                x, xn = xn, x
-            # reverse diffusion (predictors.py:66-71, sdes.py:118-123):
-            #   rev_f = theta dt (y - x) - G^2 score ; x_mean = x - rev_f ; x = x_mean + G z
-            th_dt, G = sde.discretize(t)
-            th_dt, G = float(th_dt), float(G)
-            last = (i == N - 1)
-            # the reference draws z in every predictor step (randn_like) even when it is multiplied by zero
-            z = None if (last and denoise) else draw()
-            Gz = 0.0 if probability_flow else G
-            if last:
-                backbone_stage(x, t, x_mean, 1.0 + th_dt, -th_dt, None, 0.0, -pf * G * G / std)
-                if not denoise and not probability_flow:
-                    ops.x0_noise(x_mean, ones64, z, G, x_mean)
-            else:
-                backbone_stage(x, t, xn, 1.0 + th_dt, -th_dt, z if not probability_flow else None, Gz,
-                               -pf * G * G / std)
-                x, xn = xn, x
-        out = torch.empty(B * C, L, **f32)
-        fe.istft_decompress(x_mean, L, nf, out)
-        x_hat = out.reshape(B, C, L)
+        n_draws = 1 + N * corrector_steps + N - (1 if denoise else 0)
+        key = (B * C, L, int(N), int(corrector_steps), float(snr), bool(denoise), bool(probability_flow))
+        entry = self._sgraphs.get(key)
+        if entry is None:
+            while len(self._sgraphs) >= 2:
+                self._sgraphs.popitem(last=False)
+            f32 = dict(device=dev, dtype=torch.float32)
+            mb = max(1, min(self.max_batch, 4096 // Tp))
+            spec = lambda: torch.empty(B * C, 768, Tp, 2, **f32)
+            st = dict(B=B * C, L=L, Tp=Tp, y=torch.empty(B * C, L, **f32), nf=torch.empty(B * C, **f32), Y=spec(),
+                      x=spec(), xn=spec(), x_mean=spec(), z=torch.empty(n_draws, B * C, 768, Tp, 2, **f32),
+                      out=torch.empty(B * C, L, **f32), fr=torch.empty(B * C, Tp, 1536, **f32),
+                      ones64=torch.ones(768, device=dev, dtype=torch.float64))
+            entry = dict(st=st, graph=None, warm=0,
+                         sigs={(min(B * C, lo + mb) - lo, 768, Tp) for lo in range(0, B * C, mb)})
+            self._sgraphs[key] = entry
+            self.backbone.pin_workspaces(set().union(*[e["sigs"] for e in self._sgraphs.values()]), owner=id(self))
+        else:
+            self._sgraphs.move_to_end(key)
+        st = entry["st"]
+        st["y"].copy_(y.reshape(B * C, L), non_blocking=True)
+        if noise is None:
+            st["z"].normal_(0.0, 0.5 ** 0.5)       # complex standard normal: variance 1/2 per component (randn_like)
+        else:
+            noise = list(noise)
+            if len(noise) < n_draws:
+                raise ValueError(f"the sampler makes {n_draws} draws, got {len(noise)} noise tensors")
+            for i in range(n_draws):
+                st["z"][i].copy_(torch.view_as_real(noise[i].to(dev, torch.complex64).reshape(B * C, 768, Tp)))
+        args = (st, N, corrector_steps, snr, denoise, probability_flow)
+        if entry["graph"] is not None:
+            entry["graph"].replay()
+        elif entry["warm"] == 0 or not getattr(self, "use_cuda_graph", True):
+            self._sampler(*args)                  # first call: eager (builds packed weights / temb caches)
+            entry["warm"] = 1
+        else:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._sampler(*args)
+            entry["graph"] = g
+            g.replay()
+        x_hat = st["out"].clone().reshape(B, C, L)
         for _ in range(squeeze_dims):
             x_hat = x_hat.squeeze(0)
         x_hat = x_hat.to(y_in.device)
-        info = dict(orig_length=L, normfac=nf.clone().reshape(B, C, 1), undo_pad_fn=(lambda Y_, T=1 + L // 384: Y_[..., :T]),
-                    squeeze_dims=squeeze_dims)
+        info = dict(orig_length=L, normfac=st["nf"].clone().reshape(B, C, 1),
+                    undo_pad_fn=(lambda Y_, T=1 + L // 384: Y_[..., :T]), squeeze_dims=squeeze_dims)
         return (x_hat, info) if return_preprocess_info else x_hat
 
 

@@ -92,6 +92,13 @@ def test_scoredec_pc_sampler_vs_golden(model):
     sm = ScoreModel(OUVESDE(theta=1.5, sigma_min=0.05, sigma_max=0.82, N=30), 3e-2, backbone=model.backbone,
                     feature_extractor=model.feature_extractor, sampling_rate=48000, lr=1e-4).cuda()
     x = sm.enhance(I["y"], N=2, snr=0.5, noise=I["score_draws"])
+    # second / third call: the whole sampler loop as one captured CUDA graph, then its replay
+    assert torch.equal(sm.enhance(I["y"], N=2, snr=0.5, noise=I["score_draws"]), x)
+    assert torch.equal(sm.enhance(I["y"], N=2, snr=0.5, noise=I["score_draws"]), x)
+    # Euler-Maruyama predictor = the same update for the OUVE SDE; probability flow runs and differs
+    assert torch.equal(sm.enhance(I["y"], N=2, snr=0.5, noise=I["score_draws"], predictor="euler_maruyama"), x)
+    xpf = sm.enhance(I["y"], N=2, snr=0.5, noise=I["score_draws"], probability_flow=True)
+    assert torch.isfinite(xpf).all() and not torch.equal(xpf, x)
     s = snr_db(x, gold)
     print(f"\nScoreDec PC sampler N=2: waveform SNR vs reference golden = {s:.2f} dB")
     assert x.shape == gold.shape and s >= 20.0
