@@ -211,6 +211,7 @@ class NCSNpp(nn.Module):
 
         self._prepared = None      # packed weights (built lazily, dropped on load_state_dict / .to())
         self._temb_cache = {}
+        self.generation = 0        # bumped whenever packed weights / workspaces are invalidated
         # (lane, B, F, T) -> _Workspace, least recently used first; signatures in `_pinned` (those of live CUDA
         # graphs, set by FlowModel) are never evicted, others beyond `max_workspaces` are
         self._workspaces = OrderedDict()
@@ -250,8 +251,11 @@ class NCSNpp(nn.Module):
 
     # ------------------------------------------------------------------ parameter management
     def _invalidate(self):
+        """packed weights / caches / workspaces are stale: owners of captured graphs (FlowModel, ScoreModel — several
+        may share this backbone) compare `generation` and drop their graphs"""
         self._prepared = None
         self._temb_cache = {}
+        self.generation = getattr(self, "generation", 0) + 1
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -263,9 +267,16 @@ class NCSNpp(nn.Module):
         return super()._load_from_state_dict(*a, **k)
 
     def _apply(self, fn, *a, **k):
-        self._invalidate()
-        self._workspaces = OrderedDict()
-        return super()._apply(fn, *a, **k)
+        # .cuda() / .to() on a module that is already there (e.g. a second model built around this backbone) must
+        # not invalidate buffers that captured graphs replay into: only a real move / cast does
+        w = self.output_layer.weight
+        before = (w.data_ptr(), w.device, w.dtype)
+        r = super()._apply(fn, *a, **k)
+        w = self.output_layer.weight
+        if (w.data_ptr(), w.device, w.dtype) != before:
+            self._invalidate()
+            self._workspaces = OrderedDict()
+        return r
 
     # ------------------------------------------------------------------ workspaces
     def pin_workspaces(self, sigs, owner="default"):

@@ -127,9 +127,12 @@ class FlowModel(EnhancementModel):
             self.backbone.pin_workspaces(set(), owner=id(self))
 
     def _apply(self, fn, *a, **k):
-        self.reset_cache()
-        self._streams = []
-        return super()._apply(fn, *a, **k)
+        before = (self.sigma_y.data_ptr(), self.sigma_y.device)
+        r = super()._apply(fn, *a, **k)
+        if (self.sigma_y.data_ptr(), self.sigma_y.device) != before:
+            self.reset_cache()
+            self._streams = []
+        return r
 
     def load_state_dict(self, state_dict, strict=None, **kw):
         self.reset_cache()
@@ -226,11 +229,14 @@ class FlowModel(EnhancementModel):
     def _entry(self, B, Tp, N, solver, sigma_fac, dev):
         # the micro-batch split and the lane count are baked into a captured graph
         key = (B, Tp, int(N), solver, float(sigma_fac), self._micro_batch(Tp), int(self.overlap_streams))
+        gen = getattr(self.backbone, "generation", 0)
+        if self._graphs and next(iter(self._graphs.values()))["gen"] != gen:
+            self.reset_cache()       # the (possibly shared) backbone repacked its weights / dropped its workspaces
         entry = self._graphs.get(key)
         if entry is None:
             while len(self._graphs) >= max(1, self.graph_cache_size):
                 self._graphs.popitem(last=False)
-            entry = dict(st=self._static(B, Tp, dev), graph=None, warm=0,
+            entry = dict(st=self._static(B, Tp, dev), graph=None, warm=0, gen=gen,
                          sigs={(hi - lo, 768, Tp) for lo, hi in self._chunks(B, Tp)})
             self._graphs[key] = entry
             if hasattr(self.backbone, "pin_workspaces"):
@@ -394,8 +400,11 @@ class ScoreModel(EnhancementModel):
             self.backbone.pin_workspaces(set(), owner=id(self))
 
     def _apply(self, fn, *a, **k):
-        self.reset_cache()
-        return super()._apply(fn, *a, **k)
+        gen = getattr(self.backbone, "generation", 0)
+        r = super()._apply(fn, *a, **k)
+        if getattr(self.backbone, "generation", 0) != gen:
+            self.reset_cache()
+        return r
 
     def load_state_dict(self, state_dict, strict=None, **kw):
         self.reset_cache()
@@ -481,6 +490,9 @@ class ScoreModel(EnhancementModel):
         Tp = padded_frames(1 + L // 384)
         n_draws = 1 + N * corrector_steps + N - (1 if denoise else 0)
         key = (B * C, L, int(N), int(corrector_steps), float(snr), bool(denoise), bool(probability_flow))
+        gen = getattr(self.backbone, "generation", 0)
+        if self._sgraphs and next(iter(self._sgraphs.values()))["gen"] != gen:
+            self.reset_cache()
         entry = self._sgraphs.get(key)
         if entry is None:
             while len(self._sgraphs) >= 2:
@@ -492,7 +504,7 @@ class ScoreModel(EnhancementModel):
                       x=spec(), xn=spec(), x_mean=spec(), z=torch.empty(n_draws, B * C, 768, Tp, 2, **f32),
                       out=torch.empty(B * C, L, **f32), fr=torch.empty(B * C, Tp, 1536, **f32),
                       ones64=torch.ones(768, device=dev, dtype=torch.float64))
-            entry = dict(st=st, graph=None, warm=0,
+            entry = dict(st=st, graph=None, warm=0, gen=gen,
                          sigs={(min(B * C, lo + mb) - lo, 768, Tp) for lo in range(0, B * C, mb)})
             self._sgraphs[key] = entry
             self.backbone.pin_workspaces(set().union(*[e["sigs"] for e in self._sgraphs.values()]), owner=id(self))
