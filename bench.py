@@ -382,17 +382,18 @@ def main():
                     "whole_step_frac": algo_flops_step / (ms / args.steps * 1e-3) / 1e12 / peak}
 
     # ---- secondary records (outside the headline timed region; own keys) ----
-    def timed_config(m, batch, seconds, steps=2):
+    def timed_config(m, batch, seconds, steps=2, N=None, solver=None):
         """same timing protocol (device-resident inputs, CUDA events, max over ranks) for another BASELINE config"""
+        N, solver = N or args.N, solver or args.solver
         Lc = int(seconds * SR)
         yc = synth_waveforms(batch, Lc, seed=5000 + rank * batch).to(dev)
         for _ in range(3):
-            m.enhance(yc, N=args.N, solver=args.solver)
+            m.enhance(yc, N=N, solver=solver)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(steps):
-            m.enhance(yc, N=args.N, solver=args.solver)
+            m.enhance(yc, N=N, solver=solver)
         b.record()
         barrier()
         tt = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
@@ -416,6 +417,14 @@ def main():
             m25 = m25.to(dev)
             extras["config3"] = dict(timed_config(m25, 64, 2.0), workload=f"flowdec_25s, 64 x 2 s clips, NFE {nfe}, 1 GPU")
             del m25
+            # BASELINE config 5: NFE sweep at batch 64 x 2 s (NFE 1 = Euler N=1; 2/4/8/16 = midpoint N=1/2/4/8)
+            sweep = []
+            for nfe5, (n5, s5) in ((1, (1, "euler")), (2, (1, "midpoint")), (4, (2, "midpoint")), (8, (4, "midpoint")),
+                                   (16, (8, "midpoint"))):
+                r5 = timed_config(model, 64, 2.0, steps=2, N=n5, solver=s5)
+                sweep.append({"nfe": nfe5, "solver": s5, "N": n5, "value": r5["value"], "ms_per_step": r5["ms_per_step"]})
+            extras["config5"] = {"workload": "flowdec_75m, 64 x 2 s clips, 1 GPU, NFE sweep", "unit": "audio-s/s",
+                                 "sweep": sweep}
         if world == 1:
             extras["ndac_pipeline"] = ndac_pipeline_record(model, args, dev)
         if dist is not None:
