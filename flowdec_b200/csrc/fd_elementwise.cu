@@ -596,9 +596,10 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float4* __restrict__
     const int b = tile / (wtiles * H);
     const int wx = wt * 64 + lane * 2;
     if (wx >= W) continue;
-    float acc0[8], acc1[8];
+    // packed fp32x2 accumulators (FFMA2): channel pairs (2i, 2i+1) of the octet for the two pixels
+    float2 a0[4], a1[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc0[i] = acc1[i] = sb[o * 8 + i];
+    for (int i = 0; i < 4; ++i) a0[i] = a1[i] = make_float2(sb[o * 8 + 2 * i], sb[o * 8 + 2 * i + 1]);
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int hi = h + kh - 1;
@@ -620,15 +621,19 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float4* __restrict__
         for (int ci = 0; ci < 4; ++ci) {
           const float4 wa = *reinterpret_cast<const float4*>(&sw[t * 4 + ci][o * 8]);
           const float4 wb = *reinterpret_cast<const float4*>(&sw[t * 4 + ci][o * 8 + 4]);
-          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+          const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y),
+                                make_float2(wb.z, wb.w)};
+          const float2 p0 = make_float2(xin0[ci], xin0[ci]), p1 = make_float2(xin1[ci], xin1[ci]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            acc0[i] = fmaf(xin0[ci], wv[i], acc0[i]);
-            acc1[i] = fmaf(xin1[ci], wv[i], acc1[i]);
+          for (int i = 0; i < 4; ++i) {
+            a0[i] = ffma2(p0, w2[i], a0[i]);
+            a1[i] = ffma2(p1, w2[i], a1[i]);
           }
         }
       }
     }
+    const float acc0[8] = {a0[0].x, a0[0].y, a0[1].x, a0[1].y, a0[2].x, a0[2].y, a0[3].x, a0[3].y};
+    const float acc1[8] = {a1[0].x, a1[0].y, a1[1].x, a1[1].y, a1[2].x, a1[2].y, a1[3].x, a1[3].y};
     T* op = out + ((static_cast<size_t>(b) * H + h) * W + wx) * 64 + o * 8;
     store8(op, acc0);
     if (wx + 1 < W) store8(op + 64, acc1);
