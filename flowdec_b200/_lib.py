@@ -74,7 +74,8 @@ SIGNATURES = {
     "fd_dac_conv_tc": [_P, _I, _I, ctypes.c_longlong, _I, _P, _I, _I, ctypes.POINTER(ctypes.c_int), _P, _P,
                        ctypes.c_longlong, _P, _I, _P, _P, _I, ctypes.c_longlong, _P],
     "fd_dac_final_conv": [_P, ctypes.c_longlong, _P, _P, _P, _I, _I, _I, _P],
-    "fd_dac_nct_to_ntc": [_P, _P, _I, _I, _I, _P],
+    "fd_dac_nct_to_ntc": [_P, _P, _I, _I, _I, _I, _P],
+    "fd_dac_first_conv": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "fd_stft_use_pfa": [_I],
     "fd_istft1534_decompress_pfa": [_P, _I, _I, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P],
     "fd_upfirdn2d_f32": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],

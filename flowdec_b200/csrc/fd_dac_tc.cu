@@ -319,8 +319,37 @@ __global__ void __launch_bounds__(128) dac_final_conv_kernel(const float* __rest
   out[static_cast<size_t>(b) * T + t] = tanhf(acc);
 }
 
-// [B, C, T] -> [B, T, C] (the decoder's input latent arrives channel-major from `from_codes`, as upstream)
-__global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int T) {
+// first encoder layer: Conv1d(1 -> C, k = 7, pad 3) on the waveform x [B, T] -> raw [B, T, C] and/or the Snake-activated
+// tensor (alpha of the first ResidualUnit), fp32 CUDA cores (Cin = 1: nothing for a tensor core to contract)
+__global__ void __launch_bounds__(256) dac_first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ alpha,
+                                                             float* __restrict__ raw, float* __restrict__ act, int B, int T,
+                                                             int C) {
+  const size_t total = static_cast<size_t>(B) * T * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t bt = i / C;
+    const int t = static_cast<int>(bt % T);
+    const float* xb = x + (bt - t);
+    float a = bias ? bias[c] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int tt = t + k - 3;
+      if (tt >= 0 && tt < T) a = fmaf(w[c * 7 + k], xb[tt], a);
+    }
+    if (raw) raw[i] = a;
+    if (act) {
+      const float al = alpha[c];
+      act[i] = round_tf32(snake_fast(a, 2.0f * al, 0.5f / (al + 1e-9f)));
+    }
+  }
+}
+
+// [B, C, T] -> [B, T, C] (the decoder's input latent arrives channel-major from `from_codes`, as upstream; the encoder's
+// latent goes back the same way with C and T swapped).  round_out: round to tf32 (tensors that feed a tf32 MMA)
+__global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int T,
+                                                         int round_out) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -331,7 +360,7 @@ __global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
     const int t = t0 + j, c = c0 + tx;
-    if (t < T && c < C) out[(static_cast<size_t>(b) * T + t) * C + c] = round_tf32(tile[tx][j]);   // feeds a tf32 MMA
+    if (t < T && c < C) out[(static_cast<size_t>(b) * T + t) * C + c] = round_out ? round_tf32(tile[tx][j]) : tile[tx][j];
   }
 }
 
@@ -454,8 +483,20 @@ extern "C" int fd_dac_final_conv(const float* x_act, long long x_bstride, const 
   return check_launch("fd_dac_final_conv");
 }
 
-extern "C" int fd_dac_nct_to_ntc(const float* in, float* out, int B, int C, int T, cudaStream_t stream) {
+extern "C" int fd_dac_nct_to_ntc(const float* in, float* out, int B, int C, int T, int round_tf32_out,
+                                 cudaStream_t stream) {
   FD_REQUIRE(B >= 1 && B <= 65535, "fd_dac_nct_to_ntc: B=%d", B);
-  nct_to_ntc_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), 256, 0, stream>>>(in, out, C, T);
+  nct_to_ntc_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), 256, 0, stream>>>(in, out, C, T, round_tf32_out);
   return check_launch("fd_dac_nct_to_ntc");
+}
+
+extern "C" int fd_dac_first_conv(const float* x, const float* w, const float* bias, const float* alpha, float* raw,
+                                 float* act, int B, int T, int C, cudaStream_t stream) {
+  FD_REQUIRE(raw != nullptr || act != nullptr, "fd_dac_first_conv: no output");
+  FD_REQUIRE(act == nullptr || alpha != nullptr, "fd_dac_first_conv: activated output needs alpha");
+  const size_t total = static_cast<size_t>(B) * T * C;
+  size_t g = (total + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  dac_first_conv_kernel<<<static_cast<int>(g), 256, 0, stream>>>(x, w, bias, alpha, raw, act, B, T, C);
+  return check_launch("fd_dac_first_conv");
 }

@@ -176,9 +176,12 @@ class DAC(nn.Module):
         self.tc_eligible = all(c % 32 == 0 for c in chans)
         self.precision = "tf32" if self.tc_eligible else "fp32"
         self._tc = None       # packed tf32 weights of the tensor-core decoder (built lazily on the device)
+        self._tc_enc = None   # ... and of the tensor-core encoder
+        ech = [self.encoder_dim * 2 ** i for i in range(len(self.encoder_rates) + 1)] + [self.latent_dim]
+        self.enc_tc_eligible = self._enc_ops is not None and all(c % 32 == 0 for c in ech)
 
     def _apply(self, fn, *a, **k):
-        self._tc = None
+        self._tc = self._tc_enc = None
         return super()._apply(fn, *a, **k)
 
     @property
@@ -316,7 +319,8 @@ class DAC(nn.Module):
         B, D, T = z.shape
         dev = z.device
         zt = torch.empty(B, T, D, device=dev, dtype=torch.float32)
-        _lib.check(_lib.lib().fd_dac_nct_to_ntc(_lib.ptr(z), _lib.ptr(zt), B, D, T, _lib.stream_ptr()), "fd_dac_nct_to_ntc")
+        _lib.check(_lib.lib().fd_dac_nct_to_ntc(_lib.ptr(z), _lib.ptr(zt), B, D, T, 1, _lib.stream_ptr()),
+                   "fd_dac_nct_to_ntc")
 
         def next_alpha(i):
             """Snake alpha applied to the output of layer i = the first activation of layer i + 1"""
@@ -355,6 +359,86 @@ class DAC(nn.Module):
         _lib.check(rc, "fd_dac_final_conv")
         return out
 
+    # --------------------------------------------------------------------------------------- tensor-core encoder
+    def _tc_enc_prepare(self):
+        if self._tc_enc is not None:
+            return self._tc_enc
+        from .ops import round_tf32
+
+        def conv_w(w):
+            return round_tf32(w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous())
+
+        def down_w(w, s, pad):    # [Cout, C, 2s] -> [Cout, 3*s*C]: col tap*(s*C) + j*C + ci = w[co, ci, (tap-1)*s + j + pad]
+            cout, c, k2 = w.shape
+            wp = torch.zeros(cout, 3, s, c, device=w.device, dtype=torch.float32)
+            for tap in range(3):
+                for j in range(s):
+                    k = (tap - 1) * s + j + pad
+                    if 0 <= k < k2:
+                        wp[:, tap, j, :] = w[:, :, k]
+            return round_tf32(wp.reshape(cout, 3 * s * c).contiguous())
+
+        L = []
+        for i, op in enumerate(self._enc_ops):
+            if op[0] == "conv":
+                _, w, b, a, dil, pad, _, _ = op
+                w, b, a = self._t(w), self._t(b), self._t(a)
+                if i == 0:
+                    L.append(("first", w.reshape(w.shape[0], w.shape[2]).contiguous(), b, None))
+                else:
+                    L.append(("last", conv_w(w), b, a, [j - pad for j in range(w.shape[2])]))
+            elif op[0] == "down":
+                _, w, b, a, s, pad = op
+                w, b, a = self._t(w), self._t(b), self._t(a)
+                L.append(("down", down_w(w, s, pad), b, a, s))
+            else:
+                _, (w1, b1, a1, d), (w2, b2, a2) = op
+                w1, b1, a1, w2, b2, a2 = (self._t(t) for t in (w1, b1, a1, w2, b2, a2))
+                L.append(("res", conv_w(w1), b1, a1, [(j - 3) * d for j in range(7)], conv_w(w2), b2, a2))
+        self._tc_enc = L
+        return L
+
+    def _encode_tc(self, x):
+        """Encoder on tensor cores: x [B, 1, T] -> latent z [B, D, T / hop] (same GEMM kernel as the decoder; the
+        strided convs read the activated tensor as [B, T/s, s*C], a free view of the time-major layout)"""
+        L = self._tc_enc_prepare()
+        B, _, T = x.shape
+        dev = x.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        _, w0, b0, _ = L[0]
+        C = w0.shape[0]
+        raw = torch.empty(B, T, C, **f32)
+        act = torch.empty(B, T, C, **f32)
+        _lib.check(_lib.lib().fd_dac_first_conv(_lib.ptr(x), _lib.ptr(w0), _lib.ptr(b0), _lib.ptr(L[1][3]), _lib.ptr(raw),
+                                                _lib.ptr(act), B, T, C, _lib.stream_ptr()), "fd_dac_first_conv")
+        for i in range(1, len(L)):
+            lay = L[i]
+            nxt = L[i + 1] if i + 1 < len(L) else None
+            a_next = nxt[3] if nxt is not None else None
+            need_raw = nxt is not None and nxt[0] == "res"
+            if lay[0] == "res":
+                _, w1, b1, _, offs, w2, b2, a2 = lay
+                _, h = self._tc_conv((act, 0), T, T * C, C, w1, offs, b1, None, 0, a2, C, False, True, T)
+                raw, act = self._tc_conv((h, 0), T, T * C, C, w2, [0], b2, (raw, 0), T * C, a_next, C, need_raw, True, T)
+            elif lay[0] == "down":
+                _, wp, b, _, s = lay
+                if T % s:
+                    raise ValueError(f"encoder input length must be a multiple of the hop ({self.hop_length}); call preprocess()")
+                cout = wp.shape[0]
+                raw, act = self._tc_conv((act, 0), T // s, T * C, s * C, wp, [-1, 0, 1], b, None, 0, a_next, cout,
+                                         need_raw, True, T // s)
+                T, C = T // s, cout
+            else:
+                _, wp, b, _, offs = lay
+                zt, _ = self._tc_conv((act, 0), T, T * C, C, wp, offs, b, None, 0, None, 0, True, False, T)
+                D = wp.shape[0]
+                z = torch.empty(B, D, T, **f32)
+                # [B, T, D] -> [B, D, T]: the same transpose kernel with the roles of C and T swapped, no rounding
+                _lib.check(_lib.lib().fd_dac_nct_to_ntc(_lib.ptr(zt), _lib.ptr(z), B, T, D, 0, _lib.stream_ptr()),
+                           "fd_dac_nct_to_ntc")
+                return z
+        raise RuntimeError("encoder layer list has no final conv")
+
     @torch.no_grad()
     def decode(self, z):
         """z [B, latent_dim, T] -> waveform [B, 1, ~T*hop] (dac.DAC.decode, demo.ipynb:105)"""
@@ -390,6 +474,8 @@ class DAC(nn.Module):
         x = audio_data.to(self.device, torch.float32).contiguous()
         if x.ndim != 3 or x.shape[1] != 1:
             raise ValueError(f"audio_data must be [B, 1, L], got {tuple(x.shape)}")
+        if self.precision == "tf32" and self.enc_tc_eligible:
+            return self.quantizer(self._encode_tc(x), n_quantizers)
         return self.quantizer(self._run(self._enc_ops, x), n_quantizers)
 
     @torch.no_grad()

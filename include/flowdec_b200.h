@@ -205,8 +205,15 @@ int fd_dac_conv_tc(const float* x, int B, int Tin, long long x_bstride, int Cin,
 /* last decoder layer: out[b,t] = tanh(bias[0] + sum_{k<7,c} x_act[b, t+k-3, c] * w[c,k]);  w fp32 [C,7] */
 int fd_dac_final_conv(const float* x_act, long long x_bstride, const float* w, const float* bias, float* out, int B,
                       int T, int C, fd_stream_t stream);
-/* [B,C,T] -> [B,T,C], values rounded to tf32 (the latent from fd_rvq_from_codes entering the tensor-core decoder) */
-int fd_dac_nct_to_ntc(const float* in, float* out, int B, int C, int T, fd_stream_t stream);
+/* [B,C,T] -> [B,T,C]; round_tf32_out = 1 rounds to tf32 (the latent from fd_rvq_from_codes entering the tensor-core
+ * decoder); with C and T swapped it is the way back (the encoder's latent for fd_rvq_encode) */
+int fd_dac_nct_to_ntc(const float* in, float* out, int B, int C, int T, int round_tf32_out, fd_stream_t stream);
+/* first encoder layer Conv1d(1 -> C, k7, pad 3) on x [B,T] -> raw and/or Snake-activated [B,T,C] (w fp32 [C,7]) */
+int fd_dac_first_conv(const float* x, const float* w, const float* bias, const float* alpha, float* raw, float* act,
+                      int B, int T, int C, fd_stream_t stream);
+/* Encoder down-sampling conv (k = 2s, stride s, pad p) through fd_dac_conv_tc: read the activated input [B,T,C] as
+ * [B, T/s, s*C] (a free view), offsets {-1,0,1}, wpacked[co, tap*(s*C) + j*C + ci] = w[co,ci,k] for k = (tap-1)*s + j + p
+ * inside [0, 2s) and 0 elsewhere. */
 
 /* ---- the reference's native op, as a C entry point ------------------------------------------------
  * upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1) of

@@ -274,3 +274,37 @@ def test_tc_decode_end_to_end(latent, dim, rates, nq, T):
     print(f"\nNDAC decode rel-L2 vs fp64 oracle: tensor-core tf32 {r_tc:.3e} (tf32-operand emulation of the oracle "
           f"{r_em:.3e}), CUDA-core fp32 {r_32:.3e}")
     assert r_tc <= 2.0 * r_em + 1e-4 and r_32 <= 1e-3
+
+
+@pytest.mark.parametrize("latent,edim,erates,T", [(64, 32, (2, 4), 4000), (128, 32, (2, 4, 5), 12000)])
+def test_tc_encode_end_to_end(latent, edim, erates, T):
+    """encoder on tensor cores (strided convs as 3-tap GEMMs over the [T/s, s*C] view) vs the fp64 oracle, gated on the
+    tf32-operand emulation of the oracle; the fp32 CUDA-core encoder on the same model is the A/B"""
+    drates = tuple(reversed(erates))
+    sd = D.synth_dac_state_dict(latent, 256, drates[:2], 4, seed=5, encoder_dim=edim, encoder_rates=erates)
+    model = DAC(sd, decoder_dim=256, decoder_rates=drates[:2], n_codebooks=4, latent_dim=latent, encoder_dim=edim,
+                encoder_rates=erates, sample_rate=48000).to("cuda").eval()
+    assert model.enc_tc_eligible and model.precision == "tf32"
+    g = torch.Generator().manual_seed(7)
+    audio = 0.3 * torch.randn(2, 1, T, generator=g)
+    x = model.preprocess(audio, 48000)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    with torch.no_grad():
+        z64 = D.encode(sd64, x.double(), erates)
+        c1 = F.conv1d
+        try:
+            F.conv1d = lambda a, w, b=None, **k: c1(_rt(a), _rt(w), b, **k)
+            z_em = D.encode(sd64, x.double(), erates)
+        finally:
+            F.conv1d = c1
+    z_tc = model._encode_tc(x.cuda().float().contiguous())
+    z_32 = model._run(model._enc_ops, x.cuda().float().contiguous())
+    assert z_tc.shape == z64.shape == z_32.shape
+    r_tc, r_32, r_em = rel(z_tc.cpu(), z64), rel(z_32.cpu(), z64), rel(z_em, z64)
+    print(f"\nNDAC encoder latent rel-L2 vs fp64 oracle: tensor-core tf32 {r_tc:.3e} (tf32-operand emulation {r_em:.3e}), "
+          f"CUDA-core fp32 {r_32:.3e}")
+    assert r_tc <= 2.0 * r_em + 1e-4 and r_32 <= 1e-3
+    # the public entry point runs the tensor-core encoder and the RVQ on its latent
+    zq, codes, latents, _, _ = model.encode(x.cuda(), n_quantizers=4)
+    assert codes.shape == (2, 4, z64.shape[-1]) and torch.isfinite(zq).all()
+    assert rel(model.quantizer.from_codes(codes)[0], zq) < 1e-6
