@@ -16,7 +16,8 @@ latent_dim / encoder_dim + encoder_rates, sample_rate) comes from that metadata.
 
 All arithmetic of encode / from_codes / decode runs in csrc/fd_dac.cu / csrc/fd_dac_tc.cu; there is no fallback.
 
-Decoder precision (`DAC.precision`): "tf32" (default when every channel count is a multiple of 32, as in the
+Encoder precision (`DAC.encoder_precision`): "fp32" by default (it decides discrete codes), "tf32" = the same tensor-core
+GEMM kernel as the decoder.  Decoder precision (`DAC.precision`): "tf32" (default when every channel count is a multiple of 32, as in the
 NDAC checkpoints: 1024 / 1536 / 768 / 384 / 192 / 96) runs each layer as a tcgen05 implicit GEMM on fp32
 time-major activations with tf32 operands and fp32 accumulation (residual adds in fp32); "fp32" runs the
 register-tiled CUDA-core kernels (bit-for-bit fp32 FMAs, ~50x slower).  Stated tolerance of the tf32 decoder:
@@ -179,6 +180,10 @@ class DAC(nn.Module):
         self._tc_enc = None   # ... and of the tensor-core encoder
         ech = [self.encoder_dim * 2 ** i for i in range(len(self.encoder_rates) + 1)] + [self.latent_dim]
         self.enc_tc_eligible = self._enc_ops is not None and all(c % 32 == 0 for c in ech)
+        # the encoder decides discrete codes: its default stays fp32 (codes index-identical to the fp32 oracle except at
+        # near-ties, tests/test_dac_gpu.py::_check_codes); "tf32" opts into the tensor-core encoder (latent rel-L2 2e-3 ...
+        # 7e-3 on the synthetic encoder = its tf32 floor, so a few per cent of the codes may land on a neighbouring entry)
+        self.encoder_precision = "fp32"
 
     def _apply(self, fn, *a, **k):
         self._tc = self._tc_enc = None
@@ -474,7 +479,9 @@ class DAC(nn.Module):
         x = audio_data.to(self.device, torch.float32).contiguous()
         if x.ndim != 3 or x.shape[1] != 1:
             raise ValueError(f"audio_data must be [B, 1, L], got {tuple(x.shape)}")
-        if self.precision == "tf32" and self.enc_tc_eligible:
+        if self.encoder_precision == "tf32":
+            if not self.enc_tc_eligible:
+                raise RuntimeError("encoder_precision 'tf32' needs encoder channel counts that are multiples of 32")
             return self.quantizer(self._encode_tc(x), n_quantizers)
         return self.quantizer(self._run(self._enc_ops, x), n_quantizers)
 

@@ -284,7 +284,7 @@ def test_tc_encode_end_to_end(latent, edim, erates, T):
     sd = D.synth_dac_state_dict(latent, 256, drates[:2], 4, seed=5, encoder_dim=edim, encoder_rates=erates)
     model = DAC(sd, decoder_dim=256, decoder_rates=drates[:2], n_codebooks=4, latent_dim=latent, encoder_dim=edim,
                 encoder_rates=erates, sample_rate=48000).to("cuda").eval()
-    assert model.enc_tc_eligible and model.precision == "tf32"
+    assert model.enc_tc_eligible and model.precision == "tf32" and model.encoder_precision == "fp32"
     g = torch.Generator().manual_seed(7)
     audio = 0.3 * torch.randn(2, 1, T, generator=g)
     x = model.preprocess(audio, 48000)
@@ -304,7 +304,8 @@ def test_tc_encode_end_to_end(latent, edim, erates, T):
     print(f"\nNDAC encoder latent rel-L2 vs fp64 oracle: tensor-core tf32 {r_tc:.3e} (tf32-operand emulation {r_em:.3e}), "
           f"CUDA-core fp32 {r_32:.3e}")
     assert r_tc <= 2.0 * r_em + 1e-4 and r_32 <= 1e-3
-    # the public entry point runs the tensor-core encoder and the RVQ on its latent
+    # opted in, the public entry point runs the tensor-core encoder and the RVQ on its latent
+    model.encoder_precision = "tf32"
     zq, codes, latents, _, _ = model.encode(x.cuda(), n_quantizers=4)
     assert codes.shape == (2, 4, z64.shape[-1]) and torch.isfinite(zq).all()
     assert rel(model.quantizer.from_codes(codes)[0], zq) < 1e-6
