@@ -595,14 +595,6 @@ class NCSNpp(nn.Module):
         scache.pop(out.data_ptr(), None)
         return ops.conv_direct([(a, 0, C, 1), (h, 0, C, 1)], e["wo"], e["bo"], out)
 
-    def _compact_stats(self, st, name):
-        """conv-epilogue partials [B,S,C,2] -> at most `stats_slabs` slabs (coalesced stage-1 reduce)"""
-        B, S, C, _ = st.shape
-        if S <= self.stats_slabs:
-            return st
-        out = self._ws.get(name, (B, self.stats_slabs, C, 2), torch.float32, st.device)
-        return ops.slab_reduce(st, self.stats_slabs, out)
-
     # ------------------------------------------------------------------ forward
     def velocity(self, x, y, t, out=None, base1=None, c1=0.0, base2=None, c2=0.0, coef=1.0, v_out=None,
                  lane=0, base3=None, c3=0.0):

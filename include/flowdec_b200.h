@@ -52,7 +52,8 @@ struct fd_conv_src {
  *                 (the 4-channel pyramid convs, directly or as 36 per-tap partial products)
  * bias: fp32 [npad] or NULL.  Requires W % 8 == 0 and H % (128 / min(128, pow2 divisor of W)) == 0.
  * stats (bf16 output only, may be NULL): GroupNorm partial sums of the OUTPUT, fp32
- * [B, S, cout, 2] with S = 4 * H*W/128 slabs (one per epilogue warp and tile), consumed by
+ * [B, S, cout, 2] with S = H*W/128 slabs (one per 128-pixel tile; the four epilogue warps are combined in shared
+ * memory in a fixed order), consumed by
  * fd_gn_finalize — the statistics pass of the next GroupNorm fused into this conv's epilogue.
  * max_ctas: 0 = one persistent CTA per SM.  flags bit 0: CTA pairs (cta_group::2, 256-row MMAs, weight
  * tile split across the pair) when the tile count is even; bit 1: 16x8-pixel "halo" tiles (ONE 18x10-pixel
@@ -68,7 +69,8 @@ int fd_conv2d_igemm(const struct fd_conv_src* srcs, int nsrc, const void* wpacke
  * op/upfirdn2d.cpp:38-48, op/upfirdn2d_kernel.cu:118-218). */
 /* partial[b][s][c][0..1] = sum / sum of squares of x over slab s of the HW pixels (S slabs) */
 int fd_chan_stats(const void* x_bf16, int B, int HW, int C, float* partial, int S, fd_stream_t stream);
-/* out[b][chunk][c][2] = sum over the chunk's slabs of in[b][s][c][2] (stage 1 when S is large) */
+/* out[b][chunk][c][2] = sum over the chunk's slabs of in[b][s][c][2] (optional compaction of many slabs; the backbone
+ * no longer needs it: fd_gn_finalize walks whole slabs) */
 int fd_slab_reduce(const float* in, int B, int S, int C, float* out, int chunks, fd_stream_t stream);
 /* group statistics over the virtual channel concat [part1 [B,S1,C1,2], part2 [B,S2,C2,2]] (fp64) ->
  * scale_shift fp32 [B, C1+C2, 2]:  y = x * scale + shift == GroupNorm(x) with gamma/beta */
