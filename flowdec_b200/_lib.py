@@ -40,6 +40,7 @@ _Z = ctypes.c_size_t
 SIGNATURES = {
     "fd_abi_version": [],
     "fd_conv2d_igemm": [ctypes.POINTER(ConvSrc), _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P],
+    "fd_conv_cluster4": [_I],
     "fd_chan_stats": [_P, _I, _I, _I, _P, _I, _P],
     "fd_slab_reduce": [_P, _I, _I, _I, _P, _I, _P],
     "fd_gn_finalize": [_P, _I, _I, _P, _I, _I, _I, _D, _P, _P, _I, _F, _P, _P],

@@ -538,6 +538,26 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
+// same, arriving on the barrier at this smem offset in every CTA of `cta_mask` (cluster ranks)
+__device__ __forceinline__ void umma_commit_2sm_mask(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
+// cta_group::2 TMA load multicast to the CTAs of `cta_mask`: the bytes landing in destination CTA d are counted on the
+// barrier at this offset in the LEADER of d's pair (peer bit cleared) — measured with tools/mcast_probe.py
+__device__ __forceinline__ void tma_load_2d_2sm_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+        "h"(cta_mask)
+      : "memory");
+}
+
 // one lane of a converged warp (all 32 lanes must execute this)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -532,7 +532,11 @@ struct HaloCfg {
 #endif
 constexpr int kHaloXfThreads = FD_XF_LAYOUT ? 544 : 480;
 
-template <int N, bool XF, bool TF32, int OUTC>
+// CL4: clusters of FOUR CTAs = two MMA pairs that share the weight stream: ranks 0 / 1 load their half of every weight
+// tile ONCE and multicast it to {0, 2} / {1, 3} (weights are 6.4x the A bytes on the L2 -> SM path: 590 KB vs 92 KB per
+// 128-pixel tile at 256 -> 256).  A weight slot is free when BOTH pairs' MMAs have retired it, so the pairs advance in
+// lock step on the weight ring (6 stages of slack); everything else stays per pair.
+template <int N, bool XF, bool TF32, int OUTC, bool CL4 = false>
 __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   using Cfg = HaloCfg<N, TF32, OUTC>;
   constexpr bool OUT4 = OUTC != 0;
@@ -558,8 +562,11 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();     // 0..1 (pair) or 0..3 (CL4: two pairs)
+  const uint32_t rank = crank & 1u;             // rank inside the MMA pair
+  const uint32_t lead = crank & ~1u;            // cluster rank of this pair's leader
   const bool leader_cta = (rank == 0);
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << lead);
 
   for (int i = threadIdx.x; i < N; i += blockDim.x) sBias[i] = p.bias ? p.bias[i] : 0.0f;
   if (threadIdx.x == 0) {
@@ -570,7 +577,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
     }
     for (int s = 0; s < SB; ++s) {
       mbar_init(&fullB[s], 2);
-      mbar_init(&emptyB[s], 1);
+      mbar_init(&emptyB[s], (CL4 && crank < 2) ? 2 : 1);   // the loading pair waits for both pairs' MMAs
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
   cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int tile_first = static_cast<int>((blockIdx.x >> 1) * 2 + rank);
+  const int tile_first = static_cast<int>(blockIdx.x);      // cluster c, rank r -> tile cluster_size * c + r
   const int tile_stride = static_cast<int>(gridDim.x);
   const int tiles_per_img = p.tiles_h * p.tiles_w;
 
@@ -610,7 +617,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
               tma_load_4d(sA + sa * kHaloStageBytes, &p.a_map[s], &fullA[sa], ks * kSliceC, w0 - 1, h0 - 1, n);
             } else {
               if (leader_cta) mbar_expect_tx(&readyA[sa], 2 * kHaloTxBytes);
-              else mbar_arrive_remote(&readyA[sa], 0);
+              else mbar_arrive_remote(&readyA[sa], lead);
               tma_load_4d_2sm(sA + sa * kHaloStageBytes, &p.a_map[s], &readyA[sa], ks * kSliceC, w0 - 1, h0 - 1, n);
             }
             if (++sa == SA) { sa = 0; pa ^= 1u; }
@@ -631,8 +638,12 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
               const int kcol = p.seg_kbase[s] + tap * p.seg_cin[s] + ks * kSliceC;
               mbar_wait(&emptyB[sb], pb ^ 1u);
               if (leader_cta) mbar_expect_tx(&fullB[sb], 2 * B_BYTES);
-              else mbar_arrive_remote(&fullB[sb], 0);
-              tma_load_2d_2sm(sB + sb * B_BYTES, &p.b_map, &fullB[sb], kcol, static_cast<int>(rank) * (N / 2));
+              else mbar_arrive_remote(&fullB[sb], lead);
+              if (!CL4)
+                tma_load_2d_2sm(sB + sb * B_BYTES, &p.b_map, &fullB[sb], kcol, static_cast<int>(rank) * (N / 2));
+              else if (crank < 2)     // this half of the tile goes to the same-parity CTA of both pairs
+                tma_load_2d_2sm_mcast(sB + sb * B_BYTES, &p.b_map, &fullB[sb], kcol, static_cast<int>(rank) * (N / 2),
+                                      static_cast<uint16_t>((1u << rank) | (1u << (rank + 2))));
               if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
           }
@@ -689,10 +700,11 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
                     umma_bf16_2sm(d_tmem, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
                                   idesc, (first && k == 0) ? 0u : 1u);
                 }
-                umma_commit_2sm(&emptyB[sb]);
+                // CL4: the second pair also releases the slot in the loading pair (ranks 0, 1)
+                umma_commit_2sm_mask(&emptyB[sb], (CL4 && crank == 2) ? static_cast<uint16_t>(0xF) : pair_mask);
                 if (tap == ntap - 1) {
-                  umma_commit_2sm(&emptyA[sa]);
-                  if (last_stage) umma_commit_2sm(&tfull_bar[acc]);
+                  umma_commit_2sm_mask(&emptyA[sa], pair_mask);
+                  if (last_stage) umma_commit_2sm_mask(&tfull_bar[acc], pair_mask);
                 }
               }
               __syncwarp();
@@ -749,7 +761,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           tmem_ld_wait();
           if (g == kGroups - 1) {
             tc_fence_before_sync();
-            mbar_arrive_remote(&tempty_bar[acc], 0);
+            mbar_arrive_remote(&tempty_bar[acc], lead);
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -777,7 +789,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           tmem_ld_wait();
           if (ch == kChunks - 1) {
             tc_fence_before_sync();
-            mbar_arrive_remote(&tempty_bar[acc], 0);
+            mbar_arrive_remote(&tempty_bar[acc], lead);
           }
           epilogue_chunk_f32(v, smem_u32(sBias + ch * 32), smem_u32(stg + row * 128), row,
                              stat_row ? my_stat : nullptr, lane, stat_scratch);
@@ -809,7 +821,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
           tmem_ld_wait();
           if (ch == kChunks - 1) {
             tc_fence_before_sync();
-            mbar_arrive_remote(&tempty_bar[acc], 0);
+            mbar_arrive_remote(&tempty_bar[acc], lead);
           }
           epilogue_half(v, bs + 128, rowp, row, 4, stat_row ? my_stat + 64 : nullptr, lane, stat_scratch);
         }
@@ -945,7 +957,7 @@ __global__ void __launch_bounds__(XF ? kHaloXfThreads : 224, 1) conv_halo_kernel
             if (FD_DBG) x_fence += clock64() - f0;
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive_remote_release_cluster(&readyA[sa], 0);
+          if (lane == 0) mbar_arrive_remote_release_cluster(&readyA[sa], lead);
           if (FD_DBG) x_work += clock64() - xq;
           if (++sa == SA) { sa = 0; pa ^= 1u; }
         }
@@ -1071,10 +1083,13 @@ static int launch_conv(const ConvParams& p, int max_ctas, cudaStream_t stream) {
   return check_launch("fd_conv2d_igemm");
 }
 
-template <int N, bool XF, bool TF32 = false, int OUTC = 0>
+static int g_halo_cl4 = 1;   // 4-CTA clusters with weight multicast for the bf16 N = 128 / 256 tiles (fd_conv_cluster4)
+
+template <int N, bool XF, bool TF32 = false, int OUTC = 0, bool CL4 = false>
 static int launch_halo(const HaloParams& p, int max_ctas, cudaStream_t stream) {
-  auto kern = conv_halo_kernel<N, XF, TF32, OUTC>;
+  auto kern = conv_halo_kernel<N, XF, TF32, OUTC, CL4>;
   using Cfg = HaloCfg<N, TF32, OUTC>;
+  constexpr int kCluster = CL4 ? 4 : 2;
   static bool attr_set[kMaxDevices] = {false};   // function attributes are per device
   const int dev = current_device();
   if (!attr_set[dev]) {
@@ -1083,20 +1098,32 @@ static int launch_halo(const HaloParams& p, int max_ctas, cudaStream_t stream) {
                cudaGetErrorString(e));
     attr_set[dev] = true;
   }
-  int grid = std::min(p.num_tiles, max_ctas > 0 ? max_ctas : device_sm_count()) & ~1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(XF ? kHaloXfThreads : 224);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = kCluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // persistent kernel: the grid is what can be co-resident (a GPC whose SM count is not a multiple of the cluster
+  // size leaves SMs out), never more — a second wave would double the tail
+  static int max_clusters[kMaxDevices] = {0};
+  if (!max_clusters[dev]) {
+    cfg.gridDim = dim3(kCluster * 64);
+    int n = 0;
+    cudaError_t eo = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    FD_REQUIRE(eo == cudaSuccess && n > 0, "cudaOccupancyMaxActiveClusters failed: %s", cudaGetErrorString(eo));
+    max_clusters[dev] = n;
+  }
+  int grid = std::min(p.num_tiles, max_ctas > 0 ? max_ctas : device_sm_count());
+  grid = std::min(grid, max_clusters[dev] * kCluster) / kCluster * kCluster;
+  FD_REQUIRE(grid >= kCluster, "fd_conv2d_igemm(halo): grid %d smaller than a cluster", grid);
+  cfg.gridDim = dim3(grid);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   FD_REQUIRE(e == cudaSuccess, "fd_conv2d_igemm(halo): launch failed: %s", cudaGetErrorString(e));
   return check_launch("fd_conv2d_igemm(halo)");
@@ -1117,6 +1144,13 @@ struct fd_conv_src {
                              // consumed channel: the kernel applies SiLU(x*scale+shift) to the operand
   int ss_pitch;              // channels per sample in that table (the virtual concat's width)
 };
+
+// 1 (default): bf16 halo convs run in 4-CTA clusters with weight multicast when the tile count allows; 0: CTA pairs
+extern "C" int fd_conv_cluster4(int on) {
+  const int prev = fd::g_halo_cl4;
+  fd::g_halo_cl4 = on;
+  return prev;
+}
 
 extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wpacked, int ktot,
                                const float* bias, void* out, int out_is_f32, int cout, int npad,
@@ -1215,6 +1249,12 @@ extern "C" int fd_conv2d_igemm(const fd_conv_src* srcs, int nsrc, const void* wp
                                        : launch_halo<256, false, true>(hp, max_ctas, stream);
         return any_xf ? launch_halo<128, true, true>(hp, max_ctas, stream)
                       : launch_halo<128, false, true>(hp, max_ctas, stream);
+      }
+      if (g_halo_cl4 && hp.num_tiles % 4 == 0 && hp.num_tiles >= 8) {
+        if (npad == 256) return any_xf ? launch_halo<256, true, false, 0, true>(hp, max_ctas, stream)
+                                       : launch_halo<256, false, false, 0, true>(hp, max_ctas, stream);
+        return any_xf ? launch_halo<128, true, false, 0, true>(hp, max_ctas, stream)
+                      : launch_halo<128, false, false, 0, true>(hp, max_ctas, stream);
       }
       if (npad == 256) return any_xf ? launch_halo<256, true>(hp, max_ctas, stream)
                                      : launch_halo<256, false>(hp, max_ctas, stream);

@@ -86,6 +86,11 @@ def conv_igemm(srcs, wpacked, bias, out, max_ctas=0, algo_k=None, stats=None, al
     return out
 
 
+def conv_cluster4(on):
+    """4-CTA clusters with weight multicast for the bf16 halo convs on / off; returns the previous setting"""
+    return bool(_lib.lib().fd_conv_cluster4(int(bool(on))))
+
+
 def tensor_conv_ok(B, H, W, npad, seg_channels, out_f32=False):
     """can fd_conv2d_igemm (tcgen05 tiles) take this conv?  Otherwise conv_direct (CUDA cores) runs it."""
     if W % 8 or W < 8 or any(c % 64 for c in seg_channels):

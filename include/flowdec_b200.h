@@ -63,6 +63,11 @@ int fd_conv2d_igemm(const struct fd_conv_src* srcs, int nsrc, const void* wpacke
                     const float* bias, void* out, int out_is_f32, int cout, int npad, int B, int H,
                     int W, float* stats, int max_ctas, int flags, fd_stream_t stream);
 
+/* 1 (default): the bf16 halo convolutions run in clusters of FOUR CTAs — two MMA pairs sharing one weight stream (each
+ * weight half is loaded once and TMA-multicast to the same-parity CTA of both pairs) — whenever the tile count is a
+ * multiple of 4; 0: CTA pairs only.  Returns the previous setting. */
+int fd_conv_cluster4(int on);
+
 /* ---- GroupNorm + SiLU + FIR resampling ------------------------------------------------------
  * replace nn.GroupNorm / nn.SiLU (layerspp.py:229,241,253,274; ncsnpp.py:216,228) and
  * upsample_2d / downsample_2d -> upfirdn2d (up_or_down_sampling.py:220-282,

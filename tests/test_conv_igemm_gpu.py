@@ -12,15 +12,18 @@ from flowdec_b200.ops import conv_igemm, pack_conv_weight
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[(True, True), (True, False), (False, False)],
-                ids=["halo_pair", "cta_pair", "single_cta"])
+@pytest.fixture(autouse=True, params=[(True, True, True), (True, True, False), (True, False, False), (False, False, False)],
+                ids=["halo_cluster4", "halo_pair", "cta_pair", "single_cta"])
 def _mma_variant(request):
-    """every conv test runs with 16x8 halo tiles (CTA pairs), plain CTA pairs and single-CTA MMAs"""
+    """every conv test runs with 16x8 halo tiles in 4-CTA clusters (two MMA pairs sharing a multicast weight stream),
+    halo tiles in CTA pairs, plain CTA pairs and single-CTA MMAs"""
     from flowdec_b200 import ops
     old = (ops.CTA_PAIRS, ops.HALO_TILES)
-    ops.CTA_PAIRS, ops.HALO_TILES = request.param
+    ops.CTA_PAIRS, ops.HALO_TILES, cl4 = request.param
+    old_cl4 = ops.conv_cluster4(cl4)
     yield
     ops.CTA_PAIRS, ops.HALO_TILES = old
+    ops.conv_cluster4(old_cl4)
 
 
 def _ref_conv(x_nhwc_bf16, w_oihw_bf16, bias):

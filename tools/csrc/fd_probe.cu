@@ -168,3 +168,65 @@ extern "C" int fd_umma_rate(const void* a, const void* b, long long* cycles, int
   umma_rate_kernel<<<1, 128, smem, stream>>>(ma, mb, cycles, row_off, sbo_bytes, iters);
   return check_launch("fd_umma_rate");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Probe: which mbarrier receives complete_tx for each destination of a cta_group::2 MULTICAST TMA load in a
+// cluster of 4 (two CTA pairs)?  Ranks 0 / 1 each multicast a 1 KB box to {r, r+2} with the barrier operand =
+// own barrier address with the peer bit cleared (mode 0) or unmodified (mode 1).  Leaders (0, 2) expect 2 KB,
+// non-leaders 1 KB; result[rank] = 1 if that CTA's barrier phase completed, dump = the 1 KB each CTA received.
+namespace fd {
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(32, 1)
+    mcast_probe_kernel(const __grid_constant__ CUtensorMap map, int* result, float* dump, int mode) {
+  __shared__ __align__(1024) uint8_t buf[1024];
+  __shared__ uint64_t bar;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 256; ++i) reinterpret_cast<float*>(buf)[i] = -1.0f;
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  cluster_sync_all();
+  if (threadIdx.x == 0) mbar_expect_tx(&bar, (rank & 1) ? 1024u : 2048u);
+  cluster_sync_all();                                    // every barrier armed before any copy is issued
+  if (threadIdx.x == 0) {
+    if (rank < 2) {
+      const uint32_t mb = mode == 0 ? (smem_u32(&bar) & kPeerBitMask) : smem_u32(&bar);
+      const uint16_t mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));
+      asm volatile(
+          "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+          " [%0], [%1, {%3, %4}], [%2], %5;"
+          ::"r"(smem_u32(buf)), "l"(reinterpret_cast<uint64_t>(&map)), "r"(mb), "r"(0), "r"(static_cast<int>(rank) * 8),
+            "h"(mask)
+          : "memory");
+    }
+    int done = 0;
+    for (int i = 0; i < 200000 && !done; ++i) done = mbar_test_wait(&bar, 0) ? 1 : 0;
+    result[rank] = done;
+  }
+  __syncwarp();
+  // let every in-flight copy land before anyone exits, then dump what arrived
+  for (int i = 0; i < 2000; ++i) __nanosleep(100);
+  cluster_sync_all();
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 256; ++i) dump[rank * 256 + i] = reinterpret_cast<float*>(buf)[i];
+}
+}  // namespace fd
+
+// src: fp32 [16][256] (row r holds the value r everywhere); result int[4]; dump fp32 [4][256]
+extern "C" int fd_mcast_probe(const float* src, int* result, float* dump, int mode, cudaStream_t stream) {
+  using namespace fd;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  FD_REQUIRE(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+                 qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+  EncodeTiledFn2 enc = reinterpret_cast<EncodeTiledFn2>(ptr);
+  CUtensorMap m;
+  cuuint64_t dims[2] = {32, 16};             // 32 floats (128 B) x 16 rows
+  cuuint64_t str[1] = {1024};                // row pitch 256 floats
+  cuuint32_t box[2] = {32, 8}, es[2] = {1, 1};
+  FD_REQUIRE(enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(src), dims, str, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, "encode failed");
+  mcast_probe_kernel<<<4, 32, 0, stream>>>(m, result, dump, mode);
+  return check_launch("fd_mcast_probe");
+}
