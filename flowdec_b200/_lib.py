@@ -101,6 +101,8 @@ def lib():
             fn = getattr(_lib, name)          # AttributeError here = header / library mismatch
             fn.restype = ctypes.c_int
             fn.argtypes = argtypes
+        if os.environ.get("FD_CONV_CLUSTER4") is not None:      # A/B switch for tools / bench
+            _lib.fd_conv_cluster4(int(os.environ["FD_CONV_CLUSTER4"]))
     return _lib
 
 

@@ -1083,7 +1083,11 @@ static int launch_conv(const ConvParams& p, int max_ctas, cudaStream_t stream) {
   return check_launch("fd_conv2d_igemm");
 }
 
-static int g_halo_cl4 = 1;   // 4-CTA clusters with weight multicast for the bf16 N = 128 / 256 tiles (fd_conv_cluster4)
+// 4-CTA clusters with weight multicast for the bf16 N = 128 / 256 tiles (fd_conv_cluster4).  OFF by default: measured on
+// B200 (A/B on one box, 32 x 2 s NFE 6): 123.0 vs 124.4-124.8 audio-s/s for CTA pairs.  Only 33 clusters of 4 (132 of 148
+// SMs) are co-resident because GPC SM counts are not multiples of 4; per SM the multicast kernel is ~10 % more efficient
+// (SM clock 1507 vs 1440 MHz under the same power cap), which the 11 % of idle SMs cancel.
+static int g_halo_cl4 = 0;
 
 template <int N, bool XF, bool TF32 = false, int OUTC = 0, bool CL4 = false>
 static int launch_halo(const HaloParams& p, int max_ctas, cudaStream_t stream) {
@@ -1119,6 +1123,8 @@ static int launch_halo(const HaloParams& p, int max_ctas, cudaStream_t stream) {
     cudaError_t eo = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
     FD_REQUIRE(eo == cudaSuccess && n > 0, "cudaOccupancyMaxActiveClusters failed: %s", cudaGetErrorString(eo));
     max_clusters[dev] = n;
+    if (getenv("FD_DEBUG")) fprintf(stderr, "flowdec_b200: halo<%d,%d,%d,%d> cluster %d: %d co-resident clusters (%d CTAs)\n",
+                                    N, (int)XF, (int)TF32, OUTC, kCluster, n, n * kCluster);
   }
   int grid = std::min(p.num_tiles, max_ctas > 0 ? max_ctas : device_sm_count());
   grid = std::min(grid, max_clusters[dev] * kCluster) / kCluster * kCluster;
@@ -1145,7 +1151,7 @@ struct fd_conv_src {
   int ss_pitch;              // channels per sample in that table (the virtual concat's width)
 };
 
-// 1 (default): bf16 halo convs run in 4-CTA clusters with weight multicast when the tile count allows; 0: CTA pairs
+// 1: bf16 halo convs run in 4-CTA clusters with weight multicast when the tile count allows; 0 (default): CTA pairs
 extern "C" int fd_conv_cluster4(int on) {
   const int prev = fd::g_halo_cl4;
   fd::g_halo_cl4 = on;

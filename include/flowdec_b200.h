@@ -63,9 +63,10 @@ int fd_conv2d_igemm(const struct fd_conv_src* srcs, int nsrc, const void* wpacke
                     const float* bias, void* out, int out_is_f32, int cout, int npad, int B, int H,
                     int W, float* stats, int max_ctas, int flags, fd_stream_t stream);
 
-/* 1 (default): the bf16 halo convolutions run in clusters of FOUR CTAs — two MMA pairs sharing one weight stream (each
- * weight half is loaded once and TMA-multicast to the same-parity CTA of both pairs) — whenever the tile count is a
- * multiple of 4; 0: CTA pairs only.  Returns the previous setting. */
+/* 1: the bf16 halo convolutions run in clusters of FOUR CTAs — two MMA pairs sharing one weight stream (each weight half
+ * is loaded once and TMA-multicast to the same-parity CTA of both pairs) — whenever the tile count is a multiple of 4;
+ * 0 (default): CTA pairs only (measured faster on B200: clusters of 4 leave 16 of 148 SMs idle).  Returns the previous
+ * setting. */
 int fd_conv_cluster4(int on);
 
 /* ---- GroupNorm + SiLU + FIR resampling ------------------------------------------------------
