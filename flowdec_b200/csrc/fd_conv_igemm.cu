@@ -1085,8 +1085,8 @@ static int launch_conv(const ConvParams& p, int max_ctas, cudaStream_t stream) {
 
 // 4-CTA clusters with weight multicast for the bf16 N = 128 / 256 tiles (fd_conv_cluster4).  OFF by default: measured on
 // B200 (A/B on one box, 32 x 2 s NFE 6): 123.0 vs 124.4-124.8 audio-s/s for CTA pairs.  Only 33 clusters of 4 (132 of 148
-// SMs) are co-resident because GPC SM counts are not multiples of 4; per SM the multicast kernel is ~10 % more efficient
-// (SM clock 1507 vs 1440 MHz under the same power cap), which the 11 % of idle SMs cancel.
+// SMs) are co-resident because GPC SM counts are not multiples of 4, and CTA pairs limited to 132 CTAs lose the same 1 %:
+// halving the L2 -> SM weight traffic buys nothing measurable on a power-capped step.
 static int g_halo_cl4 = 0;
 
 template <int N, bool XF, bool TF32 = false, int OUTC = 0, bool CL4 = false>
