@@ -116,6 +116,13 @@ def load_peaks():
     return 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
 
 
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p)).get("hbm_gbs", 6500.0))
+    return 6500.0
+
+
 # ------------------------------------------------------------------------------------------------
 def pick_cpu_threads():
     """the oracle's convs are MKL-DNN bound; on many-core hosts fewer threads can be faster.
@@ -239,7 +246,10 @@ def ndac_pipeline_record(model, args, dev, steps=3):
                         f"-> enhance NFE {nfe_of(args.N, args.solver)}; synthetic weights",
             "value": B * args.seconds / (sum(ms) * 1e-3), "unit": "audio-s/s", "from_codes_ms": ms[0],
             "decode_ms": ms[1], "enhance_ms": ms[2], "decode_share": ms[1] / sum(ms),
-            "decode_audio_s_per_s": B * args.seconds / (ms[1] * 1e-3)}
+            "decode_audio_s_per_s": B * args.seconds / (ms[1] * 1e-3),
+            # algorithmic HBM traffic of the decoder: 0.69 GB per audio-second (fd_dac_tc.cu row)
+            "decode_roofline": {"bound": "hbm", "unit": "GB/s", "achieved": 0.69 * B * args.seconds / (ms[1] * 1e-3),
+                                "peak": hbm_peak(), "frac": 0.69 * B * args.seconds / (ms[1] * 1e-3) / hbm_peak()}}
 
 
 # ------------------------------------------------------------------------------------------------
