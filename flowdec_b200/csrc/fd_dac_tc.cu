@@ -18,9 +18,7 @@
 //   * Snake1d of the NEXT layer (x + sin^2(a x)/(a + 1e-9)) is applied in the epilogue, which writes the raw
 //     tensor (when a later residual needs it) and/or the activated tensor; the residual add of a ResidualUnit
 //     is an fp32 add in the epilogue (exact, not a K segment, so the residual stream is never rounded).
-// warps: 0 A producer, 1 MMA issuer, 6 weight producer, 2-5 and 7-10 two epilogue groups that alternate over the
-// 32-column chunks of a tile (each warp reads its TMEM lane quarter; each group owns one staging tile).  One
-// persistent CTA per SM.
+// warps: 0 A producer, 1 MMA issuer, 2-5 epilogue, 6 weight producer.  One persistent CTA per SM.
 #include "fd_common.cuh"
 
 #include <algorithm>
@@ -51,8 +49,6 @@ struct DacTcParams {
   int alpha_mod;
   const float* residual;
   long long res_bstride;
-  float* raw_ptr;           // raw output written straight from registers when the staging tile carries the activated one
-  long long out_bstride;
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -80,9 +76,7 @@ __device__ __forceinline__ float snake_fast(float x, float two_alpha, float half
   return fmaf(1.0f - __cosf(r), half_inv, x);
 }
 
-constexpr int kDtThreads = 352;     // 11 warps
-
-__global__ void __launch_bounds__(kDtThreads, 1) dac_conv_tc_kernel(const __grid_constant__ DacTcParams p) {
+__global__ void __launch_bounds__(224, 1) dac_conv_tc_kernel(const __grid_constant__ DacTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
@@ -104,7 +98,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dac_conv_tc_kernel(const __grid
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDtSA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kDtSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
     fence_mbar_init();
     tma_prefetch_desc(&p.a_map);
     tma_prefetch_desc(&p.b_map);
@@ -187,23 +181,19 @@ __global__ void __launch_bounds__(kDtThreads, 1) dac_conv_tc_kernel(const __grid
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-  } else if (warp != 6) {
-    // ------------------------------------------------------------------ epilogue: two groups of four warps
-    const int grp = warp >= 7 ? 1 : 0;           // group 0: warps 2-5, group 1: warps 7-10
-    const int ew = warp & 3;                     // TMEM lane quarter this warp may read
+  } else if (warp < 6) {
+    const int ew = warp & 3;
     const int row = ew * 32 + lane;
-    const int et = grp * 128 + (warp - (grp ? 7 : 2)) * 32 + lane;      // 0..255 among the epilogue threads
-    const bool leader = (et == grp * 128);
-    const uint32_t bar_a = grp ? 4u : 1u, bar_b = grp ? 5u : 2u;
-    uint8_t* stg = sOut + grp * kDtOutStage;     // this group's staging tile
+    const int et = threadIdx.x - 64;             // 0..127 among the epilogue threads
+    const bool leader = (et == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles, tt = (tile / p.n_tiles) % p.t_tiles, b = tile / (p.n_tiles * p.t_tiles);
       const int n0 = nt * p.N, t = tt * kDtTile + row;
       // per-tile column parameters (the previous tile's readers are past their last use: same threads, in order)
-      named_bar_sync(3, 256);
-      for (int c = et; c < p.N; c += 256) {
+      named_bar_sync(3, 128);
+      for (int c = et; c < p.N; c += 128) {
         sBias[c] = p.bias ? p.bias[n0 + c] : 0.f;
         if (p.has_act) {
           const float a = p.alpha[(n0 + c) % p.alpha_mod];
@@ -211,36 +201,27 @@ __global__ void __launch_bounds__(kDtThreads, 1) dac_conv_tc_kernel(const __grid
           sInv[c] = 0.5f / (a + 1e-9f);
         }
       }
-      named_bar_sync(3, 256);
-      const bool in_range = t < p.T_out;
-      const float* res_row = (p.residual != nullptr && in_range)
+      named_bar_sync(3, 128);
+      const float* res_row = (p.residual != nullptr && t < p.T_out)
                                  ? p.residual + static_cast<size_t>(b) * p.res_bstride + static_cast<size_t>(t) * p.Ntot + n0
                                  : nullptr;
-      // with both outputs the raw one goes straight from registers to HBM (this lane's 128-byte row segment)
-      float* raw_row = (p.has_raw && p.has_act && in_range)
-                           ? p.raw_ptr + static_cast<size_t>(b) * p.out_bstride + static_cast<size_t>(t) * p.Ntot + n0
-                           : nullptr;
       const int chunks = p.N / 32;
-      // the residual of this group's first chunk is requested before waiting for the accumulator (its latency hides
-      // behind the MMAs); later chunks request theirs one step ahead
+      // the residual of chunk 0 is requested before waiting for the accumulator (its latency hides behind the MMAs);
+      // later chunks request theirs one chunk ahead
       float4 rr[8];
-      if (res_row != nullptr && grp < chunks) {
+      if (res_row != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rr[i] = *reinterpret_cast<const float4*>(res_row + grp * 32 + i * 4);
+        for (int i = 0; i < 8; ++i) rr[i] = *reinterpret_cast<const float4*>(res_row + i * 4);
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * 256);
-      if (grp >= chunks) {                         // nothing to read for this group (N = 32): release at once
-        tc_fence_before_sync();
-        mbar_arrive(&tempty[acc]);
-      }
 #pragma unroll 1
-      for (int ch = grp; ch < chunks; ch += 2) {
+      for (int ch = 0; ch < chunks; ++ch) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_row + ch * 32, v);
         tmem_ld_wait();
-        if (ch + 2 >= chunks) {
+        if (ch == chunks - 1) {
           tc_fence_before_sync();
           mbar_arrive(&tempty[acc]);
         }
@@ -252,15 +233,23 @@ __global__ void __launch_bounds__(kDtThreads, 1) dac_conv_tc_kernel(const __grid
           for (int i = 0; i < 8; ++i) {
             f[4 * i] += rr[i].x; f[4 * i + 1] += rr[i].y; f[4 * i + 2] += rr[i].z; f[4 * i + 3] += rr[i].w;
           }
-          if (ch + 2 < chunks) {
+          if (ch + 1 < chunks) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rr[i] = *reinterpret_cast<const float4*>(res_row + (ch + 2) * 32 + i * 4);
+            for (int i = 0; i < 8; ++i) rr[i] = *reinterpret_cast<const float4*>(res_row + (ch + 1) * 32 + i * 4);
           }
         }
-        if (raw_row != nullptr) {
+        // the TMA stores that read the staging tiles of the previous chunk must have drained them
+        if (leader) tma_store_wait_read<0>();
+        named_bar_sync(1, 128);
+        const uint32_t rowp = smem_u32(sOut + row * 128);
+        if (p.has_raw) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(raw_row + ch * 32 + i * 4) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          for (int j = 0; j < 8; ++j) {
+            uint4 q;
+            q.x = __float_as_uint(f[4 * j]); q.y = __float_as_uint(f[4 * j + 1]);
+            q.z = __float_as_uint(f[4 * j + 2]); q.w = __float_as_uint(f[4 * j + 3]);
+            sts128(rowp + static_cast<uint32_t>((j ^ (row & 7)) << 4), q);
+          }
         }
         if (p.has_act) {
 #pragma unroll
@@ -268,22 +257,19 @@ __global__ void __launch_bounds__(kDtThreads, 1) dac_conv_tc_kernel(const __grid
             // the activated tensor only ever feeds a tf32 MMA: round to nearest here (the pipe would truncate)
             f[i] = round_tf32(snake_fast(f[i], sAlpha[ch * 32 + i], sInv[ch * 32 + i]));
           }
-        }
-        // the TMA store that read this group's staging tile for its previous chunk must have drained it
-        if (leader) tma_store_wait_read<0>();
-        named_bar_sync(bar_a, 128);
-        const uint32_t rowp = smem_u32(stg + row * 128);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 q;
-          q.x = __float_as_uint(f[4 * j]); q.y = __float_as_uint(f[4 * j + 1]);
-          q.z = __float_as_uint(f[4 * j + 2]); q.w = __float_as_uint(f[4 * j + 3]);
-          sts128(rowp + static_cast<uint32_t>((j ^ (row & 7)) << 4), q);
+          for (int j = 0; j < 8; ++j) {
+            uint4 q;
+            q.x = __float_as_uint(f[4 * j]); q.y = __float_as_uint(f[4 * j + 1]);
+            q.z = __float_as_uint(f[4 * j + 2]); q.w = __float_as_uint(f[4 * j + 3]);
+            sts128(rowp + kDtOutStage + static_cast<uint32_t>((j ^ (row & 7)) << 4), q);
+          }
         }
         fence_proxy_async_smem();
-        named_bar_sync(bar_b, 128);
+        named_bar_sync(2, 128);
         if (leader) {
-          tma_store_3d(p.has_act ? &p.act_map : &p.raw_map, stg, n0 + ch * 32, tt * kDtTile, b);
+          if (p.has_raw) tma_store_3d(&p.raw_map, sOut, n0 + ch * 32, tt * kDtTile, b);
+          if (p.has_act) tma_store_3d(&p.act_map, sOut + kDtOutStage, n0 + ch * 32, tt * kDtTile, b);
           tma_store_commit();
         }
       }
@@ -455,8 +441,6 @@ extern "C" int fd_dac_conv_tc(const float* x, int B, int Tin, long long x_bstrid
   p.res_bstride = res_bstride;
   p.has_raw = out_raw != nullptr;
   p.has_act = out_act != nullptr;
-  p.raw_ptr = out_raw;
-  p.out_bstride = out_bstride;
   if (dt_make_ntc_map(&p.a_map, x, B, Tin, Cin, x_bstride, p.box_rows)) return 1;
   {
     EncodeTiledFn enc = dt_encode_fn();
@@ -481,7 +465,7 @@ extern "C" int fd_dac_conv_tc(const float* x, int B, int Tin, long long x_bstrid
   }
   const int tiles = B * p.t_tiles * p.n_tiles;
   const int grid = std::min(tiles, device_sm_count());
-  dac_conv_tc_kernel<<<grid, kDtThreads, kDtSmem, stream>>>(p);
+  dac_conv_tc_kernel<<<grid, 224, kDtSmem, stream>>>(p);
   return check_launch("fd_dac_conv_tc");
 }
 
