@@ -25,7 +25,7 @@ def halo_eligible(B, H, W, npad):
 def round_tf32(w):
     """fp32 -> nearest tf32 (10-bit mantissa) kept in fp32 words; weights are rounded once at pack time, the
     tensor pipe would otherwise truncate them"""
-    i = w.contiguous().view(torch.int32)
+    i = w.float().contiguous().view(torch.int32)
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 # when set to a list, conv_igemm appends (start_event, end_event, algorithmic_flops) per launch

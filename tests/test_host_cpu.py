@@ -130,3 +130,97 @@ def test_ragged_enhance_argument_checks():
         m.enhance(y, N=1, lengths=[96000, 96000], return_traj=True)
     with pytest.raises(RuntimeError, match="CUDA"):
         m.enhance(y, N=1, lengths=[96000, 95000])
+
+
+# ------------------------------------------------------------------------------------------------
+# round-2 host logic
+def test_backbone_plan_and_attention_keys():
+    """the static channel walk used to pack every fused weight up front, and the parameter names of the
+    7-level / bottleneck-attention configuration (must equal the reference's state_dict keys stored with the golden)"""
+    import numpy as np
+    from flowdec_b200.backbones.ncsnpp import NCSNpp
+    from flowdec_b200.model import build_flowdec
+    from oracle.make_golden import ATTN_KW
+    plan = build_flowdec("75m").backbone._plan()
+    assert len(plan) == 20 and plan[4] == [64] and plan[17] == [128, 256] and plan[31] == [256, 256] and plan[32] == [256, 64]
+    net = NCSNpp(nonlinearity="swish", attn_resolutions=[], num_channels=4, **ATTN_KW)
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ncsnpp_attn_seed4.npz"))
+    ref = {str(k): tuple(int(d) for d in str(s).split(",") if d) for k, s in zip(G["keys"], G["shapes"])}
+    mine = {"backbone." + k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert mine == ref
+    assert len(net._plan()) == 49
+    with pytest.raises(NotImplementedError):
+        NCSNpp(resblock_type="ddpm")
+    with pytest.raises(NotImplementedError):
+        NCSNpp(image_size=256, attn_resolutions=(64,))
+
+
+def test_round_tf32_and_ndac_gemm_packing():
+    """tf32 rounding helper and the GEMM forms of the NDAC layers (what fd_dac_conv_tc contracts), emulated with
+    torch on CPU: k7 dilated conv, transposed conv as the 2-tap conv with s*Cout columns, strided conv as the 3-tap
+    conv over the [T/s, s*C] view"""
+    import math
+    import torch.nn.functional as F
+    from flowdec_b200.ops import round_tf32
+    from flowdec_b200.ndac import DAC
+    from flowdec_b200.util.synth import synth_dac_state_dict
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -10, -3.14159265, 1e-30, 65504.0])
+    r = round_tf32(x)
+    assert torch.equal(r.view(torch.int32) & 0x1FFF, torch.zeros(6, dtype=torch.int32))
+    assert ((r - x).abs() <= x.abs() * 2 ** -11).all()
+
+    def gemm(xt, wp, offs, Tout):        # xt [B,T,C]; out[b,t,n] = sum_tap sum_c xt[b, t+off, c] wp[n, tap*C + c]
+        B, T, C = xt.shape
+        out = torch.zeros(B, Tout, wp.shape[0], dtype=xt.dtype)
+        for i, o in enumerate(offs):
+            idx = torch.arange(Tout) + o
+            ok = (idx >= 0) & (idx < T)
+            sl = torch.zeros(B, Tout, C, dtype=xt.dtype)
+            sl[:, ok] = xt[:, idx[ok]]
+            out += sl @ wp[:, i * C:(i + 1) * C].t()
+        return out
+
+    sd = synth_dac_state_dict(64, 128, (4, 2), 2, seed=3, encoder_dim=32, encoder_rates=(2, 4))
+    m = DAC(sd, decoder_dim=128, decoder_rates=(4, 2), n_codebooks=2, latent_dim=64, encoder_dim=32, encoder_rates=(2, 4))
+    g = torch.Generator().manual_seed(1)
+    dec = {}
+    for lay in m._tc_prepare():
+        dec.setdefault(lay[0], lay)        # first layer of each kind = m._ops[1] (convtr), m._ops[2] (res, dilation 1)
+    # transposed conv (first decoder block: 128 -> 64, s = 4, pad 2)
+    _, wp, b, a, s, pad, cout = dec["convtr"]
+    w = m._t(m._ops[1][1]).double()
+    xin = torch.randn(2, w.shape[0], 9, generator=g, dtype=torch.float64)
+    ref = F.conv_transpose1d(xin, w, None, stride=s, padding=pad)
+    z = gemm(xin.permute(0, 2, 1), wp.double(), [0, -1], xin.shape[-1] + 1).reshape(2, -1, cout)
+    got = z[:, pad:pad + ref.shape[-1]].permute(0, 2, 1)
+    assert (got - ref).abs().max() <= 2e-3 * ref.abs().max()
+    # k7 dilated conv of a residual unit
+    _, w1p, b1, a1, offs, w2p, b2, a2 = dec["res"]
+    w1 = m._t(m._ops[2][1][0]).double()
+    d = m._ops[2][1][3]
+    xin = torch.randn(2, w1.shape[1], 40, generator=g, dtype=torch.float64)
+    ref = F.conv1d(xin, w1, None, dilation=d, padding=3 * d)
+    got = gemm(xin.permute(0, 2, 1), w1p.double(), offs, 40).permute(0, 2, 1)
+    assert offs == [(j - 3) * d for j in range(7)] and (got - ref).abs().max() <= 2e-3 * ref.abs().max()
+    # strided encoder conv (32 -> 64, s = 2, pad 1) over the [T/s, s*C] view
+    enc = {}
+    for lay in m._tc_enc_prepare():
+        enc.setdefault(lay[0], lay)
+    _, wdp, bd, ad, s = enc["down"]
+    wd = m._t(next(op for op in m._enc_ops if op[0] == "down")[1]).double()
+    xin = torch.randn(2, wd.shape[1], 24, generator=g, dtype=torch.float64)
+    ref = F.conv1d(xin, wd, None, stride=s, padding=math.ceil(s / 2))
+    view = xin.permute(0, 2, 1).reshape(2, 24 // s, s * wd.shape[1])
+    got = gemm(view, wdp.double(), [-1, 0, 1], 24 // s).permute(0, 2, 1)
+    assert got.shape == ref.shape and (got - ref).abs().max() <= 2e-3 * ref.abs().max()
+
+
+def test_score_model_argument_contract():
+    from flowdec_b200.model import build_scoredec
+    sm = build_scoredec()
+    with pytest.raises(NotImplementedError):
+        sm.enhance(torch.zeros(1, 1, 24000), sampler_type="ode")
+    with pytest.raises(NotImplementedError):
+        sm.enhance(torch.zeros(1, 1, 24000), predictor="none")
+    with pytest.raises(RuntimeError):                      # CUDA only, and says so
+        sm.enhance(torch.zeros(1, 1, 24000), predictor="euler_maruyama")
