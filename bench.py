@@ -225,9 +225,12 @@ def ndac_pipeline_record(model, args, dev, steps=3):
     B = args.batch
     Tz = int(args.seconds * SR) // 640
     codes = torch.randint(0, 1024, (B, nq, Tz), generator=torch.Generator().manual_seed(3)).to(dev)
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()      # the earlier legs leave tens of GB cached: start this one from a clean allocator
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    tot = [0.0, 0.0, 0.0]
-    for it in range(steps + 2):
+    samples = []
+    for it in range(steps + 3):
         ev[0].record()
         zq, _, _ = dac.quantizer.from_codes(codes)
         ev[1].record()
@@ -236,11 +239,10 @@ def ndac_pipeline_record(model, args, dev, steps=3):
         out = model.enhance(xh, N=args.N, solver=args.solver)
         ev[3].record()
         torch.cuda.synchronize()
-        if it >= 2:
-            for i in range(3):
-                tot[i] += ev[i].elapsed_time(ev[i + 1])
+        if it >= 3:                # eager call, graph capture and first replay of enhance() are warm-up
+            samples.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
     assert torch.isfinite(out).all()
-    ms = [t / steps for t in tot]
+    ms = [sorted(s[i] for s in samples)[len(samples) // 2] for i in range(3)]      # median of the timed iterations
     model.reset_cache()
     return {"workload": f"{B} x {args.seconds:g} s: codes [B,{nq},{Tz}] -> from_codes -> decode (dim {dim}, rates {rates}) "
                         f"-> enhance NFE {nfe_of(args.N, args.solver)}; synthetic weights",
