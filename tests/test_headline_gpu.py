@@ -62,3 +62,19 @@ def test_heun2_N2_vs_golden(model):
     x = model.enhance(I["y"], N=2, solver="heun2", noise=I["eps"])
     snr, _, _ = _report("heun2 N=2 (NFE 4), 0.5 s clip", x, gold)
     assert snr >= 30.0
+
+
+def test_flowdec_25s_variant_vs_golden():
+    """BASELINE config 3's model: flowdec_25s = the same backbone with its own frequency-dependent sigma_y curve
+    (data/flowdec_autoparams_25s.npy); golden by the reference's 25s model at the headline solver setting"""
+    m = build_flowdec("25s")
+    sd = synth_state_dict(m.state_dict(), seed=0)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m75 = build_flowdec("75m")
+    assert not torch.equal(m.sigma_y.cpu(), m75.sigma_y)          # the variants differ in sigma_y only
+    I = golden_inputs()
+    gold = torch.from_numpy(np.load(GOLD)["enhance_25s_midpoint_N3"])
+    x = m.enhance(I["y"], N=3, solver="midpoint", noise=I["eps"])
+    snr, _, _ = _report("flowdec_25s midpoint N=3 (NFE 6), 0.5 s clip", x, gold)
+    assert x.shape == gold.shape and snr >= 30.0
