@@ -438,6 +438,12 @@ def main():
             extras["config5"] = {"workload": "flowdec_75m, 64 x 2 s clips, 1 GPU, NFE sweep", "unit": "audio-s/s",
                                  "sweep": sweep}
         if world == 1:
+            # secondary line: the same workload with the backbone in tf32 precision (fp32 activations, kind::tf32 MMAs)
+            model.set_precision("tf32")
+            extras["tf32_mode"] = dict(timed_config(model, B, args.seconds),
+                                       workload=f"headline workload with model.set_precision('tf32'): {B} x {args.seconds:g} s, "
+                                                f"NFE {nfe}; parity 54 dB vs the reference goldens (bf16: 37 dB)")
+            model.set_precision("bf16")
             extras["ndac_pipeline"] = ndac_pipeline_record(model, args, dev)
         if dist is not None:
             from flowdec_b200 import parallel

@@ -183,3 +183,20 @@ def test_conv_out36_gemm_first_pyramid_form(B, H, W, C, tf32):
     r = rel_l2(out.cpu().permute(0, 3, 1, 2), ref)
     print(f"\nout36 + gather C={C} tf32={tf32}: rel-L2 {r:.3e}")
     assert r <= (1.5e-3 if tf32 else 8e-3)
+
+
+def test_precise_mode_microbatches_and_lanes(model):
+    """tf32 mode through the micro-batch / two-lane machinery: a batch split over lanes equals the clips enhanced alone"""
+    from flowdec_b200.util.synth import synth_waveforms
+    y = synth_waveforms(3, 24000, seed=42)
+    eps = torch.randn(3, 1, 768, 64, dtype=torch.complex64, generator=torch.Generator().manual_seed(11))
+    old = model.max_batch
+    try:
+        model.set_precision("tf32")
+        model.max_batch = 2
+        full = model.enhance(y, N=1, solver="midpoint", noise=eps)
+        one = model.enhance(y[2:3], N=1, solver="midpoint", noise=eps[2:3])
+        assert torch.isfinite(full).all() and torch.equal(full[2:3], one)
+    finally:
+        model.max_batch = old
+        model.set_precision("bf16")
