@@ -694,12 +694,22 @@ class NCSNpp(nn.Module):
     def _forward(self, x, y, t):
         """x, y: complex64 [B,1,F,T]; t: float tensor with one element (the reference passes a
         shared scalar time, model.py:470-474).  Returns complex64 [B,1,F,T]."""
-        if torch.is_tensor(t):
-            if t.numel() != 1 and not bool((t == t.flatten()[0]).all()):
-                raise NotImplementedError("per-sample t is not supported (FlowDec inference uses a shared t)")
-            t = float(t.flatten()[0])
         xr = torch.view_as_real(x.to(torch.complex64).contiguous()).squeeze(1).contiguous()
         yr = torch.view_as_real(y.to(torch.complex64).contiguous()).squeeze(1).contiguous()
         v = torch.empty_like(xr)
+        if torch.is_tensor(t) and t.numel() != 1 and not bool((t == t.flatten()[0]).all()):
+            # per-sample times (ncsnpp.py:254 accepts t of shape [B]): samples are independent, so the batch is run in
+            # groups of equal t — the time embedding (and with it every conv0 bias) is per group, nothing else changes
+            tv = t.flatten().to(xr.device)
+            if tv.numel() != xr.shape[0]:
+                raise ValueError(f"t has {tv.numel()} entries for a batch of {xr.shape[0]}")
+            for val in torch.unique(tv).tolist():
+                idx = (tv == val).nonzero().flatten()
+                vg = torch.empty(idx.numel(), *xr.shape[1:], device=xr.device, dtype=xr.dtype)
+                self.velocity(xr.index_select(0, idx).contiguous(), yr.index_select(0, idx).contiguous(), float(val), v_out=vg)
+                v.index_copy_(0, idx, vg)
+            return torch.view_as_complex(v).unsqueeze(1)
+        if torch.is_tensor(t):
+            t = float(t.flatten()[0])
         self.velocity(xr, yr, t, v_out=v)
         return torch.view_as_complex(v).unsqueeze(1)

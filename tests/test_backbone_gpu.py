@@ -240,3 +240,18 @@ def test_caches_are_bounded_over_many_lengths(model):
     # 24000 and 24100 fall into the same 64-frame bucket -> one entry served both
     keys = {k[1] for k in model._graphs}
     assert len(keys) == len(model._graphs)
+
+
+def test_per_sample_times(model):
+    """NCSNpp.forward with one t per sample (reference ncsnpp.py:254): equal to evaluating every sample with its own
+    scalar t, bit for bit"""
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(3, 1, 768, 64, dtype=torch.complex64, generator=g).cuda()
+    y = torch.randn(3, 1, 768, 64, dtype=torch.complex64, generator=g).cuda()
+    t = torch.tensor([0.3, 0.8, 0.3]).cuda()
+    v = model.backbone(x, y, t)
+    for i in range(3):
+        vi = model.backbone(x[i:i + 1], y[i:i + 1], t[i:i + 1])
+        assert torch.equal(v[i:i + 1], vi)
+    with pytest.raises(ValueError):
+        model.backbone(x, y, torch.tensor([0.1, 0.2]).cuda())
