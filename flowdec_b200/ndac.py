@@ -201,7 +201,10 @@ class DAC(nn.Module):
     @classmethod
     def load(cls, location, *args, **kwargs):
         """audiotools.ml.BaseModel.load for package-less checkpoints: {"state_dict", "metadata": {"kwargs"}}"""
-        ckpt = torch.load(str(location), map_location="cpu", weights_only=False)
+        try:
+            ckpt = torch.load(str(location), map_location="cpu", weights_only=True)
+        except Exception:      # checkpoints that pickle non-tensor objects next to the state_dict
+            ckpt = torch.load(str(location), map_location="cpu", weights_only=False)
         kw = dict(ckpt["metadata"]["kwargs"])
         kw.update(kwargs)
         return cls(ckpt["state_dict"], **kw)
