@@ -224,3 +224,31 @@ def test_score_model_argument_contract():
         sm.enhance(torch.zeros(1, 1, 24000), predictor="none")
     with pytest.raises(RuntimeError):                      # CUDA only, and says so
         sm.enhance(torch.zeros(1, 1, 24000), predictor="euler_maruyama")
+
+
+def test_checkpoint_loaders(tmp_path):
+    """DAC.load reads audiotools-style {"state_dict", "metadata": {"kwargs"}} files; load_from_checkpoint refuses a
+    checkpoint whose backbone keys do not match instead of silently keeping random weights"""
+    from flowdec_b200.model import EnhancementModel, build_flowdec
+    from flowdec_b200.ndac import DAC
+    from flowdec_b200.util.synth import synth_dac_state_dict, synth_state_dict
+    sd = synth_dac_state_dict(64, 96, (4, 3, 2), 5, seed=1)
+    p = tmp_path / "weights.pth"
+    torch.save({"state_dict": sd, "metadata": {"kwargs": dict(decoder_dim=96, decoder_rates=[4, 3, 2], n_codebooks=5,
+                                                                latent_dim=64, sample_rate=48000)}}, p)
+    m = DAC.load(str(p))
+    assert m.decoder_rates == [4, 3, 2] and m.n_codebooks == 5 and m.sample_rate == 48000 and not m.tc_eligible
+    assert m.precision == "fp32"                      # 96 / 48 / 24 / 12 channels: the tensor-core decoder needs multiples of 32
+    fm = build_flowdec("75m")
+    good = synth_state_dict(fm.state_dict(), seed=0)
+    ck = tmp_path / "model.ckpt"
+    torch.save({"_pl_ema_state_dict": good, "state_dict": good}, ck)
+    loaded = EnhancementModel.load_from_checkpoint(str(ck), map_location="cpu")
+    assert torch.equal(loaded.state_dict()["backbone.all_modules.3.weight"], good["backbone.all_modules.3.weight"])
+    bad = {("model." + k): v for k, v in good.items()}          # wrong prefix: nothing would match
+    torch.save({"_pl_ema_state_dict": bad}, ck)
+    with pytest.raises(RuntimeError):
+        EnhancementModel.load_from_checkpoint(str(ck), map_location="cpu")
+    torch.save({"other": 1}, ck)
+    with pytest.raises(KeyError):
+        EnhancementModel.load_from_checkpoint(str(ck), map_location="cpu")
